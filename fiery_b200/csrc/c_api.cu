@@ -1,0 +1,178 @@
+// extern "C" boundary of libfiery_b200.so (declared in include/fiery_b200.h).  Argument validation, TMA descriptor
+// creation and launch dispatch; no torch types, no host<->device copies except where the header says so.
+#include <stdarg.h>
+#include <string.h>
+
+#include "lift_tile.cuh"
+
+namespace fiery {
+
+static thread_local char g_last_error[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+// ---- TMA descriptor: head tensor viewed as (channels_total = images*head_channels, h, w), innermost w ------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn() {
+    static encode_tiled_fn fn = nullptr;
+    if (fn) return fn;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<encode_tiled_fn>(sym);
+    return fn;
+}
+
+int encode_head_map(CUtensorMap* map, const void* head, int dtype, long long n_images, int head_channels, int hh, int ww) {
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    FIERY_REQUIRE(dtype == FIERY_DTYPE_F32, "TMA map: only fp32 head tensors are supported");
+    FIERY_REQUIRE((reinterpret_cast<uintptr_t>(head) & 15) == 0, "head pointer must be 16-byte aligned");
+    const size_t es = 4;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(ww), static_cast<cuuint64_t>(hh),
+                          static_cast<cuuint64_t>(n_images) * head_channels};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ww) * es, static_cast<cuuint64_t>(ww) * hh * es};
+    cuuint32_t box[3] = {WT, static_cast<cuuint32_t>(hh), CH_BOX};
+    cuuint32_t estr[3] = {1, 1, 1};
+    FIERY_REQUIRE(hh <= 256, "feat_h=%d exceeds the TMA box limit of 256", hh);
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(head), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return FIERY_OK;
+}
+
+// launchers defined next to their kernels
+int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch, cudaStream_t);
+int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, cudaStream_t);
+int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t);
+int launch_compose(int n, const float* K, const float* E, float* combined, float* translation, cudaStream_t);
+int vs_plan(int64_t n_rows, const int64_t* ranks, int32_t* seg, int64_t* host_n, cudaStream_t);
+int vs_forward(int64_t n_rows, int channels, int64_t feat_stride, const float* feats, const int64_t* coords,
+               const int32_t* seg, int64_t n_seg, float* sums, int64_t* coords_out, cudaStream_t);
+int vs_backward(int64_t n_rows, int channels, const float* grad_sums, const int32_t* seg, float* grad_feats, cudaStream_t);
+
+static int make_params(const fiery_lift_desc_t* d, const float* calib_a, const float* calib_b, const float* fu,
+                       const float* fv, const float* fd, LiftParams& P) {
+    FIERY_REQUIRE(d != nullptr, "desc is NULL");
+    FIERY_REQUIRE(d->n_frames >= 0 && d->n_cameras >= 1, "bad n_frames=%d / n_cameras=%d", d->n_frames, d->n_cameras);
+    FIERY_REQUIRE(d->depth_bins >= 1 && d->channels >= 1 && d->feat_h >= 1 && d->feat_w >= 1,
+                  "bad head shape D=%d C=%d h=%d w=%d", d->depth_bins, d->channels, d->feat_h, d->feat_w);
+    FIERY_REQUIRE(d->bev_x >= 1 && d->bev_y >= 1, "bad BEV size %dx%d", d->bev_x, d->bev_y);
+    // the reference squeezes the Z axis and assigns into (C, X, Y) (fiery.py:268-271): only one height cell works
+    FIERY_REQUIRE(d->bev_z == 1, "bev_z=%d: the reference path only supports a single height cell (fiery.py:269)", d->bev_z);
+    FIERY_REQUIRE(static_cast<long long>(d->bev_x) * d->bev_y < (1ll << 31), "BEV grid too large");
+    FIERY_REQUIRE(d->calib_mode == FIERY_CALIB_RAW || d->calib_mode == FIERY_CALIB_COMPOSED, "bad calib_mode %d", d->calib_mode);
+    FIERY_REQUIRE(d->bev_layout == FIERY_BEV_NCHW || d->bev_layout == FIERY_BEV_NHWC, "bad bev_layout %d", d->bev_layout);
+    FIERY_REQUIRE(calib_a && calib_b && fu && fv && fd, "calibration / frustum pointer is NULL");
+    for (int a = 0; a < 3; ++a) FIERY_REQUIRE(d->bev_resolution[a] > 0.f, "bev_resolution[%d] must be positive", a);
+    P.n_frames = d->n_frames; P.n_cameras = d->n_cameras;
+    P.D = d->depth_bins; P.C = d->channels; P.hh = d->feat_h; P.ww = d->feat_w;
+    P.n_wtiles = (d->feat_w + WT - 1) / WT;
+    P.use_depth = d->use_depth_distribution ? 1 : 0;
+    P.head_channels = d->channels + (P.use_depth ? d->depth_bins : 0);
+    P.calib_mode = d->calib_mode;
+    P.calib_a = calib_a; P.calib_b = calib_b; P.fu = fu; P.fv = fv; P.fd = fd;
+    P.accum = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr;
+    P.bev_layout = d->bev_layout;
+    P.pillars = static_cast<long long>(d->bev_x) * d->bev_y;
+    P.grid = make_grid_params(*d);
+    return FIERY_OK;
+}
+
+}  // namespace fiery
+
+using namespace fiery;
+
+extern "C" {
+
+FIERY_API int fiery_abi_version(void) { return FIERY_B200_ABI_VERSION; }
+
+FIERY_API const char* fiery_last_error(void) { return g_last_error; }
+
+FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
+    if (!d || d->bev_layout != FIERY_BEV_NCHW) return 0;
+    return static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y * d->channels * sizeof(float);
+}
+
+FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
+                       const float* frustum_u, const float* frustum_v, const float* frustum_d, float* bev_out,
+                       float* scratch, void* stream) {
+    LiftParams P;
+    int rc = make_params(desc, calib_a, calib_b, frustum_u, frustum_v, frustum_d, P);
+    if (rc != FIERY_OK) return rc;
+    if (P.n_frames == 0) return FIERY_OK;
+    FIERY_REQUIRE(head && bev_out, "head / bev_out is NULL");
+    FIERY_REQUIRE(desc->bev_layout == FIERY_BEV_NHWC || scratch != nullptr, "NCHW output needs the zeroed scratch buffer");
+    return launch_lift_forward(P, head, desc->head_dtype, bev_out, scratch, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
+                        const float* frustum_u, const float* frustum_v, const float* frustum_d, const float* grad_bev,
+                        void* grad_head, void* stream) {
+    LiftParams P;
+    int rc = make_params(desc, calib_a, calib_b, frustum_u, frustum_v, frustum_d, P);
+    if (rc != FIERY_OK) return rc;
+    if (P.n_frames == 0) return FIERY_OK;
+    FIERY_REQUIRE(head && grad_bev && grad_head, "head / grad_bev / grad_head is NULL");
+    P.grad_bev = grad_bev;
+    P.grad_head = static_cast<float*>(grad_head);
+    return launch_lift_backward(P, head, desc->head_dtype, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_lift_point_indices(const fiery_lift_desc_t* desc, const float* calib_a, const float* calib_b,
+                             const float* frustum_u, const float* frustum_v, const float* frustum_d, int64_t* idx_out,
+                             uint8_t* valid_out, int32_t* pillar_out, void* stream) {
+    LiftParams P;
+    int rc = make_params(desc, calib_a, calib_b, frustum_u, frustum_v, frustum_d, P);
+    if (rc != FIERY_OK) return rc;
+    return launch_point_indices(P, idx_out, valid_out, pillar_out, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_compose_calibration(int32_t n, const float* intrinsics, const float* extrinsics, float* combined_out,
+                              float* translation_out, void* stream) {
+    FIERY_REQUIRE(n >= 0, "n_matrices=%d", n);
+    FIERY_REQUIRE(n == 0 || (intrinsics && extrinsics && combined_out && translation_out), "NULL pointer");
+    return launch_compose(n, intrinsics, extrinsics, combined_out, translation_out, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_voxels_summing_plan(int64_t n_rows, const int64_t* ranks, int32_t* segment_of_row, int64_t* host_n_segments,
+                              void* stream) {
+    FIERY_REQUIRE(n_rows >= 0 && n_rows < (1ll << 31), "n_rows=%lld out of range", (long long)n_rows);
+    FIERY_REQUIRE(host_n_segments != nullptr, "host_n_segments is NULL");
+    if (n_rows == 0) { *host_n_segments = 0; return FIERY_OK; }
+    FIERY_REQUIRE(ranks && segment_of_row, "NULL pointer");
+    return vs_plan(n_rows, ranks, segment_of_row, host_n_segments, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_voxels_summing_forward(int64_t n_rows, int32_t channels, int64_t feat_stride, const float* feats,
+                                 const int64_t* coords, const int32_t* segment_of_row, int64_t n_segments,
+                                 float* sums_out, int64_t* coords_out, void* stream) {
+    FIERY_REQUIRE(n_rows >= 0 && channels >= 1 && feat_stride >= channels, "bad shape n_rows=%lld C=%d stride=%lld",
+                  (long long)n_rows, channels, (long long)feat_stride);
+    if (n_rows == 0) return FIERY_OK;
+    FIERY_REQUIRE(feats && coords && segment_of_row && sums_out && coords_out, "NULL pointer");
+    return vs_forward(n_rows, channels, feat_stride, feats, coords, segment_of_row, n_segments, sums_out, coords_out,
+                      static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_voxels_summing_backward(int64_t n_rows, int32_t channels, const float* grad_sums, const int32_t* segment_of_row,
+                                  float* grad_feats, void* stream) {
+    FIERY_REQUIRE(n_rows >= 0 && channels >= 1, "bad shape");
+    if (n_rows == 0) return FIERY_OK;
+    FIERY_REQUIRE(grad_sums && segment_of_row && grad_feats, "NULL pointer");
+    return vs_backward(n_rows, channels, grad_sums, segment_of_row, grad_feats, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+// Tile staging shared by the forward and backward lift kernels.
+//
+// Work unit ("tile"): one camera image of one frame, WT = 4 adjacent feature-map columns, all h rows, all D depth
+// bins, all C channels.  A tile is fetched from the NCHW head tensor (fiery/models/encoder.py:96 output) with 3-D TMA
+// boxes of (4 columns, h rows, 8 channels) straight into shared memory, where it lands as raw[ch][row][col].
+// The pooling loops want the transposed layouts
+//     prob[pix][d]   (pix = col*h + row, row stride dpad)            depth distribution, encoder.py:99
+//     ctx [pix][c]   (row stride C)                                 context features,  encoder.py:100
+//     pillar[pix][d] (row stride dpad)                              rank of the point, fiery.py:236-256, -1 = masked
+// so the tile is transposed in place through registers (all reads, one barrier, all writes) with a diagonal
+// lane->element mapping that keeps both sides (almost) bank-conflict free.
+#pragma once
+#include "geometry.cuh"
+
+namespace fiery {
+
+constexpr int WT = 4;        // feature-map columns per tile (16 B: the minimum TMA inner box)
+constexpr int CH_BOX = 8;    // channels per TMA box
+constexpr int CG = 16;       // channel groups of 4 -> C = 64
+
+struct LiftParams {
+    int n_frames, n_cameras;
+    int D, C, hh, ww;
+    int n_wtiles;            // ceil(ww / WT)
+    int head_channels;       // D + C, or C without the depth distribution
+    int use_depth;
+    int calib_mode;
+    const float* calib_a;
+    const float* calib_b;
+    const float* fu;         // (w) frustum pixel column coordinate   fiery.py:120
+    const float* fv;         // (h) frustum pixel row coordinate      fiery.py:122
+    const float* fd;         // (D) frustum depth                     fiery.py:115
+    float* accum;            // forward: (B', X*Y, C) channel-last accumulation target
+    const float* grad_bev;   // backward: (B', X*Y, C) or (B', C, X*Y)
+    float* grad_head;        // backward output
+    int bev_layout;
+    long long pillars;       // X*Y
+    GridParams grid;
+};
+
+template <int DBLKS>
+struct TileLayout {
+    static constexpr int DPAD = 8 * DBLKS;
+    static constexpr int PS = DPAD;              // prob row stride (floats)
+    static constexpr int NT = 64 * DBLKS;        // threads: WT columns x DBLKS depth blocks x 16 channel groups
+    static constexpr int NWARPS = NT / 32;
+
+    int hh, C, PX;                               // PX = hh * WT pixels per tile
+    // byte offsets into dynamic shared memory
+    int off_bar, off_cam, off_u, off_v, off_d, off_prob, off_ctx, off_pillar, off_chg, total;
+
+    __host__ __device__ TileLayout(int hh_, int C_) : hh(hh_), C(C_), PX(hh_ * WT) {
+        int o = 0;
+        off_bar = o;    o += 16;
+        off_cam = o;    o += 12 * 4;
+        off_u = o;      o += WT * 4;
+        off_d = o;      o += DPAD * 4;
+        off_v = o;      o += ((hh + 3) & ~3) * 4;
+        o = (o + 127) & ~127;
+        const int prob_raw = DPAD * PX * 4, prob_t = PX * PS * 4;
+        off_prob = o;   o += (prob_raw > prob_t ? prob_raw : prob_t);
+        o = (o + 127) & ~127;
+        off_ctx = o;    o += C * PX * 4;
+        o = (o + 127) & ~127;
+        off_pillar = o; o += PX * DPAD * 4;
+        off_chg = o;    o += ((PX * DBLKS + 15) & ~15);
+        total = o;
+    }
+};
+
+// ---- phase 0: constants of the tile -------------------------------------------------------------------------------
+template <int DBLKS>
+__device__ __forceinline__ void stage_constants(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem,
+                                                int cam_flat, int w0) {
+    float* s_u = reinterpret_cast<float*>(smem + L.off_u);
+    float* s_v = reinterpret_cast<float*>(smem + L.off_v);
+    float* s_d = reinterpret_cast<float*>(smem + L.off_d);
+    const int tid = threadIdx.x;
+    if (tid < WT) s_u[tid] = (w0 + tid < P.ww) ? P.fu[w0 + tid] : 0.f;
+    for (int i = tid; i < L.hh; i += blockDim.x) s_v[i] = P.fv[i];
+    for (int i = tid; i < TileLayout<DBLKS>::DPAD; i += blockDim.x) s_d[i] = (i < P.D) ? P.fd[i] : 0.f;
+    if (tid == 32) {   // one lane of warp 1 composes R @ K^-1 while warp 0 issues the TMA
+        CameraTransform T;
+        load_camera(P.calib_mode, P.calib_a, P.calib_b, cam_flat, T);
+        float* s_cam = reinterpret_cast<float*>(smem + L.off_cam);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s_cam[i] = T.m[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s_cam[9 + i] = T.t[i];
+    }
+}
+
+// ---- phase 1: pillar of every point of the tile (needs no head data; overlaps the TMA) --------------------------------
+template <int DBLKS>
+__device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem, int w0) {
+    constexpr int DPAD = TileLayout<DBLKS>::DPAD;
+    constexpr int NHS = 2;                                  // row halves, so that WT*DPAD*NHS == NT work items
+    const float* s_cam = reinterpret_cast<const float*>(smem + L.off_cam);
+    const float* s_u = reinterpret_cast<const float*>(smem + L.off_u);
+    const float* s_v = reinterpret_cast<const float*>(smem + L.off_v);
+    const float* s_d = reinterpret_cast<const float*>(smem + L.off_d);
+    int* s_pillar = reinterpret_cast<int*>(smem + L.off_pillar);
+    CameraTransform T;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) T.m[i] = s_cam[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) T.t[i] = s_cam[9 + i];
+    const GridParams& g = P.grid;
+    for (int item = threadIdx.x; item < WT * DPAD * NHS; item += blockDim.x) {
+        const int d = item % DPAD;
+        const int wt = (item / DPAD) % WT;
+        const int hs = item / (DPAD * WT);
+        const int h_lo = (L.hh * hs) / NHS, h_hi = (L.hh * (hs + 1)) / NHS;
+        int* out = s_pillar + (wt * L.hh) * DPAD + d;
+        if (d >= P.D || w0 + wt >= P.ww) {
+            for (int h = h_lo; h < h_hi; ++h) out[h * DPAD] = -1;
+            continue;
+        }
+        const float depth = s_d[d];
+        const ColumnTerms ct = column_terms(T, s_u[wt], depth);
+        for (int h = h_lo; h < h_hi; ++h) {
+            float p[3];
+            ego_point(T, ct, s_v[h], depth, p);
+            out[h * DPAD] = pillar_of(g, p);
+        }
+    }
+}
+
+// chg[pix][dblk]: bit j set <=> pillar[pix][8*dblk+j] differs from the previous row's (same column).  Row 0 -> 0.
+template <int DBLKS>
+__device__ __forceinline__ void stage_change_bits(const TileLayout<DBLKS>& L, unsigned char* smem) {
+    constexpr int DPAD = TileLayout<DBLKS>::DPAD;
+    const int* s_pillar = reinterpret_cast<const int*>(smem + L.off_pillar);
+    unsigned char* s_chg = smem + L.off_chg;
+    for (int item = threadIdx.x; item < L.PX * DBLKS; item += blockDim.x) {
+        const int dblk = item % DBLKS;
+        const int pix = item / DBLKS;               // col*hh + row
+        const int row = pix % L.hh;
+        unsigned m = 0;
+        if (row > 0) {
+            const int4* cur = reinterpret_cast<const int4*>(s_pillar + pix * DPAD + dblk * 8);
+            const int4* prv = reinterpret_cast<const int4*>(s_pillar + (pix - 1) * DPAD + dblk * 8);
+            const int4 c0 = cur[0], c1 = cur[1], p0 = prv[0], p1 = prv[1];
+            m = (c0.x != p0.x) | ((c0.y != p0.y) << 1) | ((c0.z != p0.z) << 2) | ((c0.w != p0.w) << 3) |
+                ((c1.x != p1.x) << 4) | ((c1.y != p1.y) << 5) | ((c1.z != p1.z) << 6) | ((c1.w != p1.w) << 7);
+        }
+        s_chg[item] = static_cast<unsigned char>(m);
+    }
+}
+
+// ---- TMA issue: (D/8 + C/8) boxes of (4 cols, hh rows, 8 channels) ------------------------------------------------------
+template <int DBLKS>
+__device__ __forceinline__ void issue_tile_loads(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem,
+                                                 const CUtensorMap* map, int img, int w0) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    const int box_bytes = CH_BOX * L.PX * 4;
+    const int n_dbox = P.use_depth ? DBLKS : 0;
+    const int n_cbox = L.C / CH_BOX;
+    mbar_arrive_expect_tx(bar, static_cast<uint32_t>((n_dbox + n_cbox) * box_bytes));
+    const int ch_base = img * P.head_channels;
+    for (int i = 0; i < n_dbox; ++i)
+        tma_load_3d(smem + L.off_prob + i * box_bytes, map, bar, w0, 0, ch_base + i * CH_BOX);
+    const int ctx0 = P.use_depth ? P.D : 0;
+    for (int i = 0; i < n_cbox; ++i)
+        tma_load_3d(smem + L.off_ctx + i * box_bytes, map, bar, w0, 0, ch_base + ctx0 + i * CH_BOX);
+}
+
+// ---- phase 2: softmax over depth + in-place transposes ---------------------------------------------------------------
+// Warp-specialised, one "unit" per warp, all units run concurrently (host checks units <= warps):
+//   * depth unit  (one per block of 32 raw pixels): lane l owns raw pixel p0+l and reads its DPAD logits on the
+//     diagonal d = (l+k) mod DPAD -- bank = ((PX+1)*l + PX*k) mod 32 is a bijection in l because PX is a multiple of 4,
+//     so the reads are conflict free; max / exp / sum are order independent, so the softmax (encoder.py:99) is lane
+//     local; the probabilities are stored to prob[pixT][d] after the barrier.
+//   * context unit (one per 32 channels x 32 raw pixels): same diagonal; stores to ctx[pixT][c] hit bank c mod 32,
+//     conflict free for C = 64.
+// All raw values are held in registers across one __syncthreads(), so the transposes are in place.
+template <int DBLKS>
+__device__ __forceinline__ void transform_tile(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem) {
+    constexpr int DPAD = TileLayout<DBLKS>::DPAD;
+    constexpr int PS = TileLayout<DBLKS>::PS;
+    float* s_prob = reinterpret_cast<float*>(smem + L.off_prob);
+    float* s_ctx = reinterpret_cast<float*>(smem + L.off_ctx);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int PX = L.PX, hh = L.hh;
+    const int n_pblk = (PX + 31) >> 5;
+    const int n_cblk = L.C >> 5;
+
+    const bool depth_unit = warp < n_pblk;
+    const bool ctx_unit = !depth_unit && warp < n_pblk * (1 + n_cblk);
+    const int pblk = depth_unit ? warp : (warp - n_pblk) % n_pblk;
+    const int c0 = ctx_unit ? ((warp - n_pblk) / n_pblk) * 32 : 0;
+    const int pix = pblk * 32 + lane;                       // raw pixel index row*WT + col
+    const bool active = (depth_unit || ctx_unit) && pix < PX;
+    const int pixT = active ? (pix % WT) * hh + pix / WT : 0;   // transposed pixel index col*hh + row
+
+    float v[DPAD > 32 ? DPAD : 32];
+    if (depth_unit && active) {
+        if (P.use_depth) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < DPAD; ++k) {
+                int d = lane + k;
+                d = (d >= DPAD) ? d - DPAD : d;
+                v[k] = (d < P.D) ? s_prob[d * PX + pix] : -INFINITY;
+                mx = fmaxf(mx, v[k]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < DPAD; ++k) {
+                v[k] = (v[k] == -INFINITY) ? 0.f : expf(v[k] - mx);          // encoder.py:99
+                sum += v[k];
+            }
+            const float inv = __fdiv_rn(1.0f, sum);
+#pragma unroll
+            for (int k = 0; k < DPAD; ++k) v[k] *= inv;
+        } else {
+#pragma unroll
+            for (int k = 0; k < DPAD; ++k) {                                 // encoder.py:102: every depth gets ctx
+                int d = lane + k;
+                d = (d >= DPAD) ? d - DPAD : d;
+                v[k] = (d < P.D) ? 1.0f : 0.f;
+            }
+        }
+    } else if (ctx_unit && active) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = s_ctx[(c0 + ((lane + k) & 31)) * PX + pix];
+    }
+    __syncthreads();      // every raw value is in registers: both regions may now be overwritten
+
+    if (depth_unit && active) {
+#pragma unroll
+        for (int k = 0; k < DPAD; ++k) {
+            int d = lane + k;
+            d = (d >= DPAD) ? d - DPAD : d;
+            s_prob[pixT * PS + d] = v[k];
+        }
+    } else if (ctx_unit && active) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) s_ctx[pixT * L.C + c0 + ((lane + k) & 31)] = v[k];
+    }
+    __syncthreads();
+}
+
+}  // namespace fiery

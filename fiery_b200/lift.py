@@ -1,0 +1,293 @@
+"""The fused camera->BEV lift behind the reference's call signatures.
+
+Reference call sites replaced:
+  (B3) ``Fiery.calculate_birds_eye_view_features(x, intrinsics, extrinsics) -> (b, s, C, X, Y)``
+       fiery/models/fiery.py:275-286 -- everything after ``Encoder.depth_layer`` (encoder.py:96) runs in the CUDA
+       library: get_geometry (fiery.py:193-208), the softmax x context outer product (encoder.py:98-102) and
+       projection_to_birds_eye_view / VoxelsSumming (fiery.py:221-273, geometry.py:283-314).
+  (B1) ``VoxelsSumming.apply`` -- see fiery_b200/geometry.py.
+
+``LiftSplat`` carries what ``Fiery.__init__`` builds for this path (fiery.py:18-29): the frustum and the three BEV
+grid tensors, under the same names, so a reference ``state_dict`` loads into it unchanged.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .geometry import (_require_cuda, _stream_ptr, bev_offset_fp32, calculate_birds_eye_view_parameters, create_frustum,
+                       split_frustum, z_valid_interval)
+
+_TORCH_TO_DTYPE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
+
+
+def pack_sequence_dim(x: torch.Tensor) -> torch.Tensor:
+    """(b, s, ...) -> (b*s, ...); fiery/utils/network.py:5-7."""
+    b, s = x.shape[:2]
+    return x.view(b * s, *x.shape[2:])
+
+
+def unpack_sequence_dim(x: torch.Tensor, b: int, s: int) -> torch.Tensor:
+    """(b*s, ...) -> (b, s, ...); fiery/utils/network.py:10-11."""
+    return x.view(b, s, *x.shape[1:])
+
+
+class _ScratchPool:
+    """Zero-initialised accumulation buffers, one per (device, stream, size).  The kernels leave a buffer all-zero
+    again when they finish (include/fiery_b200.h), so it is allocated and cleared once."""
+
+    def __init__(self):
+        self._bufs: Dict[Tuple[int, int, int], torch.Tensor] = {}
+
+    def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
+        key = (device.index if device.index is not None else torch.cuda.current_device(),
+               torch.cuda.current_stream(device).cuda_stream, nbytes)
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
+            self._bufs[key] = buf
+        return buf
+
+    def clear(self) -> None:
+        self._bufs.clear()
+
+
+_scratch = _ScratchPool()
+
+
+class LiftSplat(nn.Module):
+    """Frustum + BEV grid constants of the lift and its forward/backward entry points.
+
+    Parameter names (``frustum``, ``bev_resolution``, ``bev_start_position``, ``bev_dimension``) and shapes are those
+    of ``Fiery`` (fiery/models/fiery.py:21-23,128) so reference checkpoints keep loading.
+    """
+
+    def __init__(self, x_bound=(-50.0, 50.0, 0.5), y_bound=(-50.0, 50.0, 0.5), z_bound=(-10.0, 10.0, 20.0),
+                 d_bound=(2.0, 50.0, 1.0), final_dim=(224, 480), encoder_downsample: int = 8, out_channels: int = 64,
+                 use_depth_distribution: bool = True, output_layout: str = "contiguous", calibration: str = "fused"):
+        super().__init__()
+        res, start, dim = calculate_birds_eye_view_parameters(list(x_bound), list(y_bound), list(z_bound))
+        self.bev_resolution = nn.Parameter(res, requires_grad=False)
+        self.bev_start_position = nn.Parameter(start, requires_grad=False)
+        self.bev_dimension = nn.Parameter(dim, requires_grad=False)
+        self.frustum = nn.Parameter(create_frustum(tuple(final_dim), encoder_downsample, list(d_bound)), requires_grad=False)
+        self.encoder_out_channels = out_channels
+        self.use_depth_distribution = use_depth_distribution
+        if output_layout not in ("contiguous", "channels_last"):
+            raise ValueError("output_layout must be 'contiguous' (what the reference returns) or 'channels_last'")
+        if calibration not in ("fused", "torch"):
+            raise ValueError("calibration must be 'fused' (R @ K^-1 composed in the kernel) or 'torch'")
+        self.output_layout = output_layout
+        self.calibration = calibration
+        self._consts = None     # cached device-side constants, rebuilt when parameters move / change
+
+    @classmethod
+    def from_config(cls, cfg, **kw) -> "LiftSplat":
+        """``cfg``: a fiery_b200.synthetic.LiftConfig, or a reference CfgNode-like object with LIFT / IMAGE / MODEL."""
+        if hasattr(cfg, "LIFT"):
+            return cls(cfg.LIFT.X_BOUND, cfg.LIFT.Y_BOUND, cfg.LIFT.Z_BOUND, cfg.LIFT.D_BOUND, cfg.IMAGE.FINAL_DIM,
+                       cfg.MODEL.ENCODER.DOWNSAMPLE, cfg.MODEL.ENCODER.OUT_CHANNELS,
+                       cfg.MODEL.ENCODER.USE_DEPTH_DISTRIBUTION, **kw)
+        return cls(cfg.x_bound, cfg.y_bound, cfg.z_bound, cfg.d_bound, cfg.final_dim, cfg.downsample, cfg.out_channels,
+                   cfg.use_depth_distribution, **kw)
+
+    @classmethod
+    def from_fiery(cls, model, **kw) -> "LiftSplat":
+        """Adopts the constants of an instantiated reference ``Fiery`` module (shares nothing, copies values)."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.bev_resolution = nn.Parameter(model.bev_resolution.detach().clone(), requires_grad=False)
+        self.bev_start_position = nn.Parameter(model.bev_start_position.detach().clone(), requires_grad=False)
+        self.bev_dimension = nn.Parameter(model.bev_dimension.detach().clone(), requires_grad=False)
+        self.frustum = nn.Parameter(model.frustum.detach().clone(), requires_grad=False)
+        self.encoder_out_channels = int(model.encoder_out_channels)
+        enc = getattr(model, "encoder", None)
+        self.use_depth_distribution = bool(getattr(enc, "use_depth_distribution", True))
+        self.output_layout = kw.get("output_layout", "contiguous")
+        self.calibration = kw.get("calibration", "fused")
+        self._consts = None
+        return self
+
+    # -- constants ------------------------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._consts = None
+        return super()._apply(fn, *a, **k)
+
+    def _constants(self, device: torch.device):
+        c = self._consts
+        if c is not None and c["device"] == device:
+            return c
+        u, v, d = split_frustum(self.frustum)
+        dim = [int(x) for x in self.bev_dimension.detach().cpu().tolist()]
+        res = self.bev_resolution.detach().float().cpu().numpy().astype(np.float32)
+        off = bev_offset_fp32(self.bev_start_position, self.bev_resolution)
+        z_lo, z_hi = z_valid_interval(float(res[2]), dim[2])
+        c = dict(device=device, u=u.to(device), v=v.to(device), d=d.to(device), dim=dim, res=res, off=off,
+                 z_lo=float(z_lo), z_hi=float(z_hi), D=int(d.numel()), h=int(v.numel()), w=int(u.numel()))
+        self._consts = c
+        return c
+
+    def _desc(self, c, n_frames: int, n_cameras: int, head_dtype: torch.dtype, calib_mode: int, layout: int) -> _lib.LiftDesc:
+        if head_dtype not in _TORCH_TO_DTYPE:
+            raise _lib.FieryError(f"head dtype {head_dtype} is not supported (float32 / float16)")
+        d = _lib.LiftDesc()
+        d.n_frames, d.n_cameras = n_frames, n_cameras
+        d.depth_bins, d.channels = c["D"], self.encoder_out_channels
+        d.feat_h, d.feat_w = c["h"], c["w"]
+        d.bev_x, d.bev_y, d.bev_z = c["dim"]
+        for a in range(3):
+            d.bev_offset[a] = float(c["off"][a])
+            d.bev_resolution[a] = float(c["res"][a])
+        d.z_valid_lo, d.z_valid_hi = c["z_lo"], c["z_hi"]
+        d.use_depth_distribution = 1 if self.use_depth_distribution else 0
+        d.head_dtype = _TORCH_TO_DTYPE[head_dtype]
+        d.calib_mode = calib_mode
+        d.bev_layout = layout
+        return d
+
+    def _calibration(self, intrinsics: torch.Tensor, extrinsics: torch.Tensor):
+        """Returns (calib_mode, a, b) device tensors for the C ABI."""
+        if self.calibration == "torch":
+            # the reference's own expression (fiery.py:196,203) on the inputs' device; inv_ex avoids the host sync of
+            # torch.inverse's error check and runs the same LAPACK/cuSOLVER routine
+            rotation, translation = extrinsics[..., :3, :3], extrinsics[..., :3, 3]
+            combined = rotation.matmul(torch.linalg.inv_ex(intrinsics).inverse)
+            return _lib.CALIB_COMPOSED, combined.float().contiguous(), translation.float().contiguous()
+        return _lib.CALIB_RAW, intrinsics.float().contiguous(), extrinsics.float().contiguous()
+
+    # -- public entry points --------------------------------------------------------------------------------------
+    def forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:
+        """head (B'*n, D+C, h, w) [= Encoder.depth_layer output, encoder.py:96], intrinsics (B', n, 3, 3),
+        extrinsics (B', n, 4, 4) -> BEV features (B', C, X, Y) float32 (fiery.py:225-227 allocates float32)."""
+        return _LiftSplatFunction.apply(head, intrinsics, extrinsics, self)
+
+    def point_indices(self, intrinsics: torch.Tensor, extrinsics: torch.Tensor):
+        """Integer voxel coordinates of every frustum point, as the reference computes them at fiery.py:236-256.
+        Returns (idx (B', N, 3) int64, valid (B', N) bool, pillar (B', N) int32 [rank, or -1 if masked])."""
+        _require_cuda(intrinsics, "intrinsics")
+        lib = _lib.load()
+        dev = intrinsics.device
+        c = self._constants(dev)
+        B, n = intrinsics.shape[:2]
+        mode, a, b = self._calibration(intrinsics, extrinsics)
+        desc = self._desc(c, B, n, torch.float32, mode, _lib.BEV_NCHW)
+        N = n * c["D"] * c["h"] * c["w"]
+        idx = torch.empty((B, N, 3), dtype=torch.int64, device=dev)
+        valid = torch.empty((B, N), dtype=torch.uint8, device=dev)
+        pillar = torch.empty((B, N), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.fiery_lift_point_indices(desc, a.data_ptr(), b.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
+                                                    c["d"].data_ptr(), idx.data_ptr(), valid.data_ptr(),
+                                                    pillar.data_ptr(), _stream_ptr(dev)), "fiery_lift_point_indices")
+        return idx, valid.bool(), pillar
+
+    def compose_calibration(self, intrinsics: torch.Tensor, extrinsics: torch.Tensor):
+        """combined = R @ inverse(K) and translation (fiery.py:196,203) from the device kernel."""
+        _require_cuda(intrinsics, "intrinsics")
+        lib = _lib.load()
+        dev = intrinsics.device
+        K = intrinsics.float().contiguous()
+        E = extrinsics.float().contiguous()
+        lead = K.shape[:-2]
+        n = int(np.prod(lead)) if len(lead) else 1
+        comb = torch.empty(lead + (3, 3), dtype=torch.float32, device=dev)
+        trans = torch.empty(lead + (3,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.fiery_compose_calibration(n, K.data_ptr(), E.data_ptr(), comb.data_ptr(), trans.data_ptr(),
+                                                     _stream_ptr(dev)), "fiery_compose_calibration")
+        return comb, trans
+
+    # -- raw launches (used by the autograd function and by bench.py) ------------------------------------------------
+    def _launch_forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:
+        _require_cuda(head, "head")
+        lib = _lib.load()
+        dev = head.device
+        c = self._constants(dev)
+        if intrinsics.dim() != 4 or extrinsics.dim() != 4:
+            raise ValueError("intrinsics must be (B', n, 3, 3) and extrinsics (B', n, 4, 4)")
+        B, n = intrinsics.shape[:2]
+        C = self.encoder_out_channels
+        ch = C + (c["D"] if self.use_depth_distribution else 0)
+        if tuple(head.shape) != (B * n, ch, c["h"], c["w"]):
+            raise ValueError(f"head must be {(B * n, ch, c['h'], c['w'])}, got {tuple(head.shape)}")
+        head = head.contiguous()
+        mode, a, b = self._calibration(intrinsics.to(dev), extrinsics.to(dev))
+        X, Y, _ = c["dim"]
+        with torch.cuda.device(dev):
+            if self.output_layout == "channels_last":
+                desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NHWC)
+                store = torch.zeros((B, X, Y, C), dtype=torch.float32, device=dev)
+                out, scratch_ptr = store.permute(0, 3, 1, 2), 0
+            else:
+                desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NCHW)
+                store = torch.empty((B, C, X, Y), dtype=torch.float32, device=dev)
+                out = store
+                scratch_ptr = _scratch.get(dev, int(lib.fiery_lift_scratch_bytes(desc))).data_ptr() if B else 0
+            _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
+                                              c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
+                                              _stream_ptr(dev)), "fiery_lift_forward")
+        return out
+
+    def _launch_backward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
+                         grad_bev: torch.Tensor) -> torch.Tensor:
+        lib = _lib.load()
+        dev = head.device
+        c = self._constants(dev)
+        B, n = intrinsics.shape[:2]
+        head = head.contiguous()
+        mode, a, b = self._calibration(intrinsics.to(dev), extrinsics.to(dev))
+        g = grad_bev.float()
+        if g.permute(0, 2, 3, 1).is_contiguous() and not g.is_contiguous():
+            layout = _lib.BEV_NHWC
+        else:
+            layout = _lib.BEV_NCHW
+            g = g.contiguous()
+        desc = self._desc(c, B, n, head.dtype, mode, layout)
+        grad_head = torch.empty_like(head)
+        with torch.cuda.device(dev):
+            _lib.check(lib.fiery_lift_backward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
+                                               c["v"].data_ptr(), c["d"].data_ptr(), g.data_ptr(), grad_head.data_ptr(),
+                                               _stream_ptr(dev)), "fiery_lift_backward")
+        return grad_head
+
+
+class _LiftSplatFunction(torch.autograd.Function):
+    """autograd node of the fused lift: saves the head tensor and the calibration (recomputing softmax and voxel indices
+    in backward is cheaper than saving the 124 MB/frame frustum volume the reference keeps alive)."""
+
+    @staticmethod
+    def forward(ctx, head, intrinsics, extrinsics, module: LiftSplat):
+        out = module._launch_forward(head, intrinsics, extrinsics)
+        ctx.module = module
+        ctx.save_for_backward(head, intrinsics, extrinsics)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_bev):
+        head, intrinsics, extrinsics = ctx.saved_tensors
+        grad_head = ctx.module._launch_backward(head, intrinsics, extrinsics, grad_bev)
+        return grad_head, None, None, None     # calibration is data: no gradient (geometry.py:300)
+
+
+def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):
+    """Replacement for ``Fiery.calculate_birds_eye_view_features`` (fiery/models/fiery.py:275-286), same signature:
+    x (b, s, n, 3, H, W), intrinsics (b, s, n, 3, 3), extrinsics (b, s, n, 4, 4) -> (b, s, C, X, Y).
+
+    ``self`` is the reference ``Fiery`` module; its backbone and ``depth_layer`` (library convolutions,
+    encoder.py:94-96) run unchanged, everything after them runs in the fused CUDA lift."""
+    b, s, n, c, h, w = x.shape
+    x = pack_sequence_dim(x)
+    intrinsics = pack_sequence_dim(intrinsics)
+    extrinsics = pack_sequence_dim(extrinsics)
+    enc = self.encoder
+    head = enc.depth_layer(enc.get_features(x.view(b * s * n, c, h, w)))          # encoder.py:94-96
+    lift = getattr(self, "_fiery_b200_lift", None)
+    if lift is None:
+        lift = LiftSplat.from_fiery(self).to(head.device)
+        object.__setattr__(self, "_fiery_b200_lift", lift)
+    bev = lift(head, intrinsics, extrinsics)
+    return unpack_sequence_dim(bev, b, s)

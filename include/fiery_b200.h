@@ -1,0 +1,143 @@
+/*
+ * fiery_b200 -- C ABI of the Blackwell-native (sm_100a) camera->BEV lift.
+ *
+ * The reference (wayveai/fiery) has no FFI: its "operator API" for this path is three Python call sites
+ * (SURVEY.md section 8b).  Each entry point below replaces one of them and is what a binding for the path would
+ * bind (ctypes stub: fiery_b200/_lib.py; reference-side patch: INTEGRATION.md):
+ *
+ *   fiery_lift_forward / fiery_lift_backward
+ *       replace Fiery.get_geometry              fiery/models/fiery.py:193-208
+ *             + Encoder.forward tail            fiery/models/encoder.py:98-102   (softmax x context outer product)
+ *             + Fiery.projection_to_birds_eye_view   fiery/models/fiery.py:221-273
+ *       i.e. the body of Fiery.calculate_birds_eye_view_features (fiery.py:275-286) after depth_layer.
+ *   fiery_voxels_summing_forward / _backward
+ *       replace VoxelsSumming.forward/backward  fiery/utils/geometry.py:283-314  (call site fiery.py:261)
+ *   fiery_lift_point_indices
+ *       exposes the integer voxel coordinates the reference computes at fiery.py:236-256 (for parity checks)
+ *   fiery_compose_calibration
+ *       exposes combined = R @ inverse(K), translation  (fiery.py:196,203)
+ *
+ * Conventions: every pointer is a DEVICE pointer on the current CUDA device unless its name starts with
+ * `host_`; tensors are dense row-major with the shapes given; `stream` is a cudaStream_t passed as void*
+ * (NULL = default stream).  Calls enqueue work and return without synchronising unless stated.  Return value:
+ * 0 on success, a negative FIERY_E_* code otherwise; fiery_last_error() gives the message for the calling thread.
+ * There is no CPU implementation behind this ABI.
+ */
+#ifndef FIERY_B200_H_
+#define FIERY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FIERY_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FIERY_API __attribute__((visibility("default")))
+#else
+#define FIERY_API
+#endif
+
+enum {
+    FIERY_OK = 0,
+    FIERY_E_INVALID = -1,     /* bad argument / unsupported shape (message says which) */
+    FIERY_E_CUDA = -2,        /* a CUDA runtime/driver call failed */
+    FIERY_E_UNSUPPORTED = -3  /* valid request this build does not implement */
+};
+
+enum { FIERY_DTYPE_F32 = 0, FIERY_DTYPE_F16 = 1 };
+
+/* How the camera calibration is supplied (fiery.py:193-205). */
+enum {
+    FIERY_CALIB_RAW = 0,       /* calib_a = intrinsics (B',n,3,3), calib_b = extrinsics (B',n,4,4); R @ K^-1 is
+                                  composed on the device (LU with partial pivoting + solve, explicit fp32 order) */
+    FIERY_CALIB_COMPOSED = 1   /* calib_a = combined (B',n,3,3) = R @ K^-1, calib_b = translation (B',n,3) */
+};
+
+/* Memory layout of the BEV tensor produced / consumed. Logical shape is always (B', C, X, Y) (fiery.py:225). */
+enum {
+    FIERY_BEV_NCHW = 0,        /* contiguous (B', C, X, Y) -- what the reference returns */
+    FIERY_BEV_NHWC = 1         /* physical (B', X, Y, C): torch "channels_last" for the same logical tensor */
+};
+
+typedef struct fiery_lift_desc {
+    int32_t n_frames;          /* B' = batch x time receptive field (fiery.py:278) */
+    int32_t n_cameras;         /* n */
+    int32_t depth_bins;        /* D, len(arange(*LIFT.D_BOUND)) (fiery.py:115) */
+    int32_t channels;          /* C, MODEL.ENCODER.OUT_CHANNELS */
+    int32_t feat_h, feat_w;    /* h, w = FINAL_DIM // DOWNSAMPLE (fiery.py:112) */
+    int32_t bev_x, bev_y, bev_z;   /* bev_dimension (geometry.py:55); bev_z must be 1 (fiery.py:269) */
+    float bev_offset[3];       /* bev_start_position - bev_resolution / 2, evaluated in fp32 (fiery.py:236) */
+    float bev_resolution[3];   /* geometry.py:53 */
+    float z_valid_lo, z_valid_hi; /* closed fp32 interval of (z - bev_offset[2]) for which
+                                     0 <= trunc((z - bev_offset[2]) / bev_resolution[2]) < bev_z; computed
+                                     exactly on the host (fiery_b200/geometry.py) */
+    int32_t use_depth_distribution;  /* encoder.py:98: 1 = softmax x context, 0 = uniform depth (head has C channels) */
+    int32_t head_dtype;        /* FIERY_DTYPE_* of the head tensor */
+    int32_t calib_mode;        /* FIERY_CALIB_* */
+    int32_t bev_layout;        /* FIERY_BEV_* */
+} fiery_lift_desc_t;
+
+FIERY_API int fiery_abi_version(void);
+FIERY_API const char* fiery_last_error(void);
+
+/* Bytes of zero-initialised device scratch fiery_lift_forward needs for FIERY_BEV_NCHW output (0 for NHWC).
+ * Invariant: the scratch must be all zero on entry; it is all zero again when the call's work completes. */
+FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* desc);
+
+/*
+ * Forward lift.  head: (B'*n, D+C, h, w) [C channels if !use_depth_distribution], dtype head_dtype.
+ * frustum_u (w), frustum_v (h), frustum_d (D): the separable factors of Fiery.frustum (fiery.py:109-128), fp32.
+ * bev_out: (B',C,X,Y) fp32 in bev_layout.  For FIERY_BEV_NHWC the caller must pass bev_out zero-filled (the kernel
+ * accumulates into it) and scratch may be NULL.
+ */
+FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
+                       const float* frustum_u, const float* frustum_v, const float* frustum_d,
+                       float* bev_out, float* scratch, void* stream);
+
+/*
+ * Backward of the lift w.r.t. the head tensor.  grad_bev: (B',C,X,Y) fp32 in bev_layout; grad_head: same shape and
+ * dtype as head, fully overwritten.  Calibration gets no gradient (geometry is integer, geometry.py:300).
+ */
+FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
+                        const float* frustum_u, const float* frustum_v, const float* frustum_d,
+                        const float* grad_bev, void* grad_head, void* stream);
+
+/*
+ * Integer voxel coordinates of all N = n*D*h*w points per frame, in the reference's point order
+ * (camera, depth, row, column) (fiery.py:233).  idx_out: (B',N,3) int64 = trunc((p - offset)/res) (fiery.py:236-237);
+ * valid_out: (B',N) uint8 (fiery.py:240-247); pillar_out: (B',N) int32 = rank (fiery.py:252-256) or -1 -- taken
+ * from the same device function the lift kernels use.  Any output pointer may be NULL.
+ */
+FIERY_API int fiery_lift_point_indices(const fiery_lift_desc_t* desc, const float* calib_a, const float* calib_b,
+                             const float* frustum_u, const float* frustum_v, const float* frustum_d,
+                             int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, void* stream);
+
+/* combined (B'*n,3,3) and translation (B'*n,3) from intrinsics (B'*n,3,3) and extrinsics (B'*n,4,4). */
+FIERY_API int fiery_compose_calibration(int32_t n_matrices, const float* intrinsics, const float* extrinsics,
+                              float* combined_out, float* translation_out, void* stream);
+
+/*
+ * VoxelsSumming.forward (geometry.py:286-302).  feats (Nm,C) fp32 with row stride feat_stride elements,
+ * coords (Nm,3) int64, ranks (Nm) int64 sorted ascending.
+ * Step 1 -- fiery_voxels_summing_plan: writes segment_of_row (Nm) int32 (the index into the output each row sums
+ * into) and *host_n_segments = U.  Synchronises `stream` (the reference's boolean indexing at geometry.py:295 has
+ * the same host sync).  Step 2 -- fiery_voxels_summing_forward: sums_out (U,C) fp32, coords_out (U,3) int64 (coords
+ * of the last row of each run, geometry.py:295).
+ * Backward (geometry.py:305-314): grad_feats[i] = grad_sums[segment_of_row[i]].
+ */
+FIERY_API int fiery_voxels_summing_plan(int64_t n_rows, const int64_t* ranks, int32_t* segment_of_row,
+                              int64_t* host_n_segments, void* stream);
+FIERY_API int fiery_voxels_summing_forward(int64_t n_rows, int32_t channels, int64_t feat_stride, const float* feats,
+                                 const int64_t* coords, const int32_t* segment_of_row, int64_t n_segments,
+                                 float* sums_out, int64_t* coords_out, void* stream);
+FIERY_API int fiery_voxels_summing_backward(int64_t n_rows, int32_t channels, const float* grad_sums,
+                                  const int32_t* segment_of_row, float* grad_feats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIERY_B200_H_ */
