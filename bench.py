@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the camera->BEV lift (BASELINE.json metric: lift frames/sec, 6-cam 224x480 -> 200x200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3_baseline]
+
+One "step" = one pass of the hot path {head tensor, intrinsics, extrinsics} -> BEV (B', C, X, Y) over one batch of
+synthetic frames.  Prints ONE JSON line (rank 0).
+
+  value      whole-job frames/s, inputs resident in HBM, through the public Python API (LiftSplat.forward -> C ABI)
+  e2e        same metric with HOST (pinned) inputs and a host copy of the BEV inside the timed region
+  roofline   the dominant kernel (lift_forward_kernel) against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle's torch-CPU restatement of the reference op chain on this box's host cores, bounded sample
+
+`--impl reference` times that CPU restatement itself (the reference is pure PyTorch; /root/reference is not on the GPU
+box, oracle/lift_oracle.py restates it op for op and is pinned to it by oracle/gen_golden.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from fiery_b200.synthetic import CONFIGS, LiftConfig, make_calibration, make_grad_bev, make_head
+
+METRIC = "camera->BEV lift frames/sec (6-cam 224x480 -> 200x200)"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_lift_once(oracle, head, K, E):
+    return oracle.lift(head, K, E)
+
+
+def time_cpu_reference(cfg: LiftConfig, frames: int, reps: int, warmup: int = 1):
+    """Times the oracle's torch-CPU restatement of the reference op chain (fiery.py:193-273, encoder.py:99-100,
+    geometry.py:283-314) with all host threads.  Returns (frames_per_s, seconds_per_call, threads)."""
+    from oracle import lift_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sub = LiftConfig(**{**cfg.__dict__, "frames": frames})
+    K, E = make_calibration(sub, seed=0)
+    K, E = torch.from_numpy(K), torch.from_numpy(E)
+    head = torch.from_numpy(make_head(sub, seed=0))
+    oracle = O.LiftOracle.from_config(sub)
+    with torch.no_grad():
+        for _ in range(warmup):
+            cpu_lift_once(oracle, head, K, E)
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            cpu_lift_once(oracle, head, K, E)
+            ts.append(time.perf_counter() - t0)
+    sec = float(np.median(ts))
+    return frames / sec, sec, torch.get_num_threads()
+
+
+def run_reference(args, cfg: LiftConfig, rank: int):
+    if rank != 0:
+        return
+    frames = min(cfg.frames, 3)
+    steps = max(1, args.steps)
+    fps, sec, threads = time_cpu_reference(cfg, frames, reps=steps, warmup=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg.name, "frames_per_step": frames, "n_cameras": cfg.n_cameras,
+                   "final_dim": list(cfg.final_dim), "bev": list(cfg.bev_hw), "direction": "forward"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} reps of {frames} frame(s) of {cfg.name}, torch-CPU op chain of the reference "
+                                   f"(oracle/lift_oracle.py), {threads} threads"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default="cfg3_baseline", choices=sorted(CONFIGS))
+    ap.add_argument("--layout", default="contiguous", choices=["contiguous", "channels_last"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--cpu-reps", type=int, default=5)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.workload]
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: fiery_b200 has no CPU path")
+    import torch.distributed as dist
+    from fiery_b200 import _lib
+    from fiery_b200.geometry import _stream_ptr
+    from fiery_b200.lift import LiftSplat
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- per-rank shard: weak scaling, every rank lifts its own B' frames ------------------------
+    frames = cfg.frames
+    K, E = make_calibration(cfg, seed=100 + rank)
+    head_np = make_head(cfg, seed=100 + rank)
+    lift = LiftSplat.from_config(cfg, output_layout=args.layout).to(dev)
+    K_d, E_d = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
+    head_d = torch.from_numpy(head_np).to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    W, S = max(args.warmup, 3), max(args.steps, 1)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_steps(step_fn, n_steps):
+        """Per-step CUDA events on the current stream; L2 flushed (256 MiB write) before each step, outside the events."""
+        times = []
+        for _ in range(n_steps):
+            flush.fill_(1.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            b.synchronize()
+            times.append(a.elapsed_time(b))
+        return times
+
+    # ---- value: device-resident inputs through the public API ----------------------------------------------------------
+    def step_device():
+        with torch.no_grad():
+            return lift(head_d, K_d, E_d)
+
+    for _ in range(W):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_dev = timed_steps(step_device, S)
+    barrier()
+
+    # ---- e2e: pinned host inputs, host copy of the result, all inside the timed region ---------------------------------
+    head_h = torch.from_numpy(head_np).pin_memory()
+    K_h, E_h = torch.from_numpy(K).pin_memory(), torch.from_numpy(E).pin_memory()
+    X, Y = cfg.bev_hw
+    out_h = torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        with torch.no_grad():
+            h = head_h.to(dev, non_blocking=True)
+            k = K_h.to(dev, non_blocking=True)
+            e = E_h.to(dev, non_blocking=True)
+            out_h.copy_(lift(h, k, e), non_blocking=True)
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t_e2e = timed_steps(step_e2e, S)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline: the lift kernel alone (C ABI, channel-last target already zeroed), events on the launch stream -------
+    lib = _lib.load()
+    c = lift._constants(dev)
+    desc = lift._desc(c, frames, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, _lib.BEV_NHWC)
+    acc = torch.zeros((frames, X, Y, cfg.out_channels), dtype=torch.float32, device=dev)
+    stream = _stream_ptr(dev)
+
+    def lift_kernel_only():
+        _lib.check(lib.fiery_lift_forward(desc, head_d.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(),
+                                          c["v"].data_ptr(), c["d"].data_ptr(), acc.data_ptr(), 0, stream), "fiery_lift_forward")
+
+    for _ in range(3):
+        lift_kernel_only()
+    t_kernel = timed_steps(lift_kernel_only, S)
+    barrier()
+
+    def reduce_max(x):
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_dev = reduce_max(float(np.mean(t_dev)))
+    ms_e2e = reduce_max(float(np.mean(t_e2e)))
+    ms_kernel = reduce_max(float(np.mean(t_kernel)))
+    total_frames = frames * world
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        alg_bytes = cfg.fwd_bytes_per_frame() * frames
+        achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": S,
+            "warmup": W, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg.name, "frames_per_step_per_gpu": frames, "n_cameras": cfg.n_cameras,
+                       "final_dim": list(cfg.final_dim), "feat_hw": list(cfg.feat_hw), "depth_bins": cfg.depth_bins,
+                       "channels": cfg.out_channels, "bev": [X, Y], "direction": "forward", "output_layout": args.layout,
+                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                       "l2": "flushed before every timed step (256 MiB write); step time = CUDA events around the step",
+                       "timing": "mean over steps, max over ranks"},
+            "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(head_h.numel() * 4 + K_h.numel() * 4 + E_h.numel() * 4),
+                    "d2h_bytes_per_step": int(out_h.numel() * 4)},
+            "gpu_launches": (1 if args.layout == "channels_last" else 2) * S,
+            "roofline": {"bound": "hbm", "kernel": "lift_forward_kernel", "achieved": achieved, "peak": peak,
+                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel,
+                         "step_frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / peak},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            fps, sec, threads = time_cpu_reference(cfg, min(frames, args.cpu_frames), reps=args.cpu_reps)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_reps} reps of {min(frames, args.cpu_frames)} frame(s) of {cfg.name}: "
+                                              f"torch-CPU op chain of the reference (oracle/lift_oracle.py), median"}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""CPU: host-side logic, the C ABI surface, and the no-fallback rule."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import fiery_b200
+from fiery_b200 import _lib
+from fiery_b200.geometry import (VoxelsSumming, bev_offset_fp32, calculate_birds_eye_view_parameters, create_frustum,
+                                 split_frustum, z_valid_interval)
+from fiery_b200.lift import LiftSplat
+from fiery_b200.synthetic import CONFIGS, make_calibration, shard_frames
+from oracle import lift_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function include/fiery_b200.h declares is exported by the built shared library with a ctypes signature."""
+    header = open(os.path.join(ROOT, "include", "fiery_b200.h")).read()
+    declared = set(re.findall(r"FIERY_API\s+[\w\s\*]+?\b(fiery_\w+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.fiery_abi_version() == _lib.ABI_VERSION
+
+
+def test_desc_struct_matches_header_layout():
+    # 9 int32, 6 float, 2 float, 4 int32 = 21 x 4 bytes
+    assert ctypes.sizeof(_lib.LiftDesc) == 21 * 4
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    d = _lib.LiftDesc()
+    d.n_frames, d.n_cameras, d.depth_bins, d.channels, d.feat_h, d.feat_w = 1, 1, 48, 64, 8, 16
+    d.bev_x, d.bev_y, d.bev_z = 50, 50, 2          # two height cells: the reference cannot do that either (fiery.py:269)
+    for a in range(3):
+        d.bev_resolution[a] = 1.0
+    rc = lib.fiery_lift_forward(d, 16, 16, 16, 16, 16, 16, 16, 16, None)
+    assert rc == -1 and b"bev_z" in lib.fiery_last_error()
+    assert lib.fiery_lift_scratch_bytes(d) == 1 * 50 * 50 * 64 * 4
+    n = ctypes.c_int64(-1)
+    assert lib.fiery_voxels_summing_plan(0, None, None, ctypes.byref(n), None) == 0 and n.value == 0
+
+
+def test_no_cpu_fallback():
+    """The product path refuses CPU tensors instead of silently computing on the host."""
+    m = LiftSplat.from_config(CONFIGS["cfg1_tiny"])
+    cfg = CONFIGS["cfg1_tiny"]
+    K, E = make_calibration(cfg)
+    head = torch.zeros(cfg.frames * cfg.n_cameras, cfg.head_channels, *cfg.feat_hw)
+    with pytest.raises(_lib.FieryError):
+        m(head, torch.from_numpy(K), torch.from_numpy(E))
+    with pytest.raises(_lib.FieryError):
+        VoxelsSumming.apply(torch.zeros(4, 8), torch.zeros(4, 3, dtype=torch.long), torch.zeros(4, dtype=torch.long))
+
+
+def test_product_code_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "fiery_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no CPU", ""), f"{f} mentions the oracle"
+
+
+def test_host_constants_match_oracle():
+    for cfg in CONFIGS.values():
+        r, s, d = calculate_birds_eye_view_parameters(cfg.x_bound, cfg.y_bound, cfg.z_bound)
+        ro, so, do = O.bev_grid(cfg.x_bound, cfg.y_bound, cfg.z_bound)
+        assert torch.equal(r, ro) and torch.equal(s, so) and torch.equal(d, do)
+        fr = create_frustum(cfg.final_dim, cfg.downsample, cfg.d_bound)
+        assert torch.equal(fr, O.frustum_grid(cfg.final_dim, cfg.downsample, cfg.d_bound))
+        u, v, dd = split_frustum(fr)
+        assert u.numel() == cfg.feat_hw[1] and v.numel() == cfg.feat_hw[0] and dd.numel() == cfg.depth_bins
+        off = bev_offset_fp32(s, r)
+        assert np.array_equal(off, (so - ro / 2.0).numpy())
+    with pytest.raises(ValueError):
+        bad = create_frustum((64, 128), 8, (2.0, 50.0, 1.0)).clone()
+        bad[3, 2, 1, 0] += 1.0
+        split_frustum(bad)
+
+
+@pytest.mark.parametrize("res,dim", [(20.0, 1), (0.5, 200), (0.3, 7), (1.7, 3)])
+def test_z_valid_interval_is_exact(res, dim):
+    """[lo, hi] is exactly the set of fp32 a with 0 <= trunc(a / res) < dim (fiery.py:236-247 on the z axis)."""
+    lo, hi = z_valid_interval(res, dim)
+    r = np.float32(res)
+
+    def ok(a):
+        q = np.float32(a) / r
+        return q > -1 and int(np.trunc(q)) >= 0 and int(np.trunc(q)) < dim
+
+    assert ok(lo) and ok(hi)
+    assert not ok(np.nextafter(lo, np.float32(-np.inf), dtype=np.float32))
+    assert not ok(np.nextafter(hi, np.float32(np.inf), dtype=np.float32))
+    rng = np.random.default_rng(0)
+    for a in rng.uniform(-2 * res, (dim + 1) * res, size=2000).astype(np.float32):
+        assert ok(a) == (lo <= a <= hi)
+
+
+def test_state_dict_names_match_reference():
+    """fiery.py:21-23,128: the four non-trainable parameters the reference keeps in its state_dict."""
+    m = LiftSplat()
+    assert set(m.state_dict()) == {"bev_resolution", "bev_start_position", "bev_dimension", "frustum"}
+    assert all(not p.requires_grad for p in m.parameters())
+
+
+def test_shard_frames_partitions():
+    for n in (1, 9, 12, 72):
+        for ws in (1, 2, 4, 8):
+            parts = [list(shard_frames(n, ws, r)) for r in range(ws)]
+            assert sorted(sum(parts, [])) == list(range(n))
+            assert max(map(len, parts)) - min(map(len, parts)) <= 1
