@@ -34,28 +34,44 @@ static encode_tiled_fn get_encode_fn() {
     return fn;
 }
 
-int encode_head_map(CUtensorMap* map, const void* head, int dtype, long long n_images, int head_channels, int hh, int ww) {
+// One 4-D view (column, row, channel-within-image, image) of `channels` channels starting at channel `ch0` of every image.
+static int encode_view(CUtensorMap* map, const void* head, long long n_images, int head_channels, int ch0, int channels,
+                       int hh, int ww) {
     encode_tiled_fn fn = get_encode_fn();
     if (!fn) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    FIERY_REQUIRE(dtype == FIERY_DTYPE_F32, "TMA map: only fp32 head tensors are supported");
-    FIERY_REQUIRE((reinterpret_cast<uintptr_t>(head) & 15) == 0, "head pointer must be 16-byte aligned");
     const size_t es = 4;
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(ww), static_cast<cuuint64_t>(hh),
-                          static_cast<cuuint64_t>(n_images) * head_channels};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(ww) * es, static_cast<cuuint64_t>(ww) * hh * es};
-    cuuint32_t box[3] = {WT, static_cast<cuuint32_t>(hh), CH_BOX};
-    cuuint32_t estr[3] = {1, 1, 1};
+    const char* base = static_cast<const char*>(head) + static_cast<size_t>(ch0) * hh * ww * es;
+    FIERY_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "head tensor (or its context slice) is not 16-byte aligned");
     FIERY_REQUIRE(hh <= 256, "feat_h=%d exceeds the TMA box limit of 256", hh);
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(head), dims, strides, box, estr,
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(ww), static_cast<cuuint64_t>(hh), static_cast<cuuint64_t>(channels),
+                          static_cast<cuuint64_t>(n_images)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(ww) * es, static_cast<cuuint64_t>(ww) * hh * es,
+                             static_cast<cuuint64_t>(ww) * hh * head_channels * es};
+    cuuint32_t box[4] = {WT, static_cast<cuuint32_t>(hh), CH_BOX, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<char*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return FIERY_OK;
 }
 
+int encode_head_maps(HeadMaps* maps, const void* head, int dtype, const LiftParams& P) {
+    FIERY_REQUIRE(dtype == FIERY_DTYPE_F32, "TMA map: only fp32 head tensors are supported");
+    const long long n_images = static_cast<long long>(P.n_frames) * P.n_cameras;
+    int rc = FIERY_OK;
+    if (P.use_depth) {
+        rc = encode_view(&maps->depth, head, n_images, P.head_channels, 0, P.D, P.hh, P.ww);
+        if (rc != FIERY_OK) return rc;
+    } else {
+        memset(&maps->depth, 0, sizeof(CUtensorMap));
+    }
+    return encode_view(&maps->ctx, head, n_images, P.head_channels, P.use_depth ? P.D : 0, P.C, P.hh, P.ww);
+}
+
 // launchers defined next to their kernels
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch, cudaStream_t);
-int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, cudaStream_t);
+int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, float* workspace, cudaStream_t);
 int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t);
 int launch_compose(int n, const float* K, const float* E, float* combined, float* translation, cudaStream_t);
 int vs_plan(int64_t n_rows, const int64_t* ranks, int32_t* seg, int64_t* host_n, cudaStream_t);
@@ -75,7 +91,8 @@ static int make_params(const fiery_lift_desc_t* d, const float* calib_a, const f
     FIERY_REQUIRE(static_cast<long long>(d->bev_x) * d->bev_y < (1ll << 31), "BEV grid too large");
     FIERY_REQUIRE(d->calib_mode == FIERY_CALIB_RAW || d->calib_mode == FIERY_CALIB_COMPOSED, "bad calib_mode %d", d->calib_mode);
     FIERY_REQUIRE(d->bev_layout == FIERY_BEV_NCHW || d->bev_layout == FIERY_BEV_NHWC, "bad bev_layout %d", d->bev_layout);
-    FIERY_REQUIRE(calib_a && calib_b && fu && fv && fd, "calibration / frustum pointer is NULL");
+    FIERY_REQUIRE(d->n_frames == 0 || (calib_a && calib_b), "calibration pointer is NULL");
+    FIERY_REQUIRE(fu && fv && fd, "frustum pointer is NULL");
     for (int a = 0; a < 3; ++a) FIERY_REQUIRE(d->bev_resolution[a] > 0.f, "bev_resolution[%d] must be positive", a);
     P.n_frames = d->n_frames; P.n_cameras = d->n_cameras;
     P.D = d->depth_bins; P.C = d->channels; P.hh = d->feat_h; P.ww = d->feat_w;
@@ -106,6 +123,11 @@ FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
     return static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y * d->channels * sizeof(float);
 }
 
+FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* d) {
+    if (!d || d->bev_layout != FIERY_BEV_NCHW) return 0;
+    return static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y * d->channels * sizeof(float);
+}
+
 FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                        const float* frustum_u, const float* frustum_v, const float* frustum_d, float* bev_out,
                        float* scratch, void* stream) {
@@ -120,7 +142,7 @@ FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head
 
 FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                         const float* frustum_u, const float* frustum_v, const float* frustum_d, const float* grad_bev,
-                        void* grad_head, void* stream) {
+                        void* grad_head, float* workspace, void* stream) {
     LiftParams P;
     int rc = make_params(desc, calib_a, calib_b, frustum_u, frustum_v, frustum_d, P);
     if (rc != FIERY_OK) return rc;
@@ -128,7 +150,9 @@ FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* hea
     FIERY_REQUIRE(head && grad_bev && grad_head, "head / grad_bev / grad_head is NULL");
     P.grad_bev = grad_bev;
     P.grad_head = static_cast<float*>(grad_head);
-    return launch_lift_backward(P, head, desc->head_dtype, static_cast<cudaStream_t>(stream));
+    FIERY_REQUIRE(desc->bev_layout == FIERY_BEV_NHWC || workspace != nullptr,
+                  "NCHW grad_bev needs a workspace of fiery_lift_workspace_bytes()");
+    return launch_lift_backward(P, head, desc->head_dtype, workspace, static_cast<cudaStream_t>(stream));
 }
 
 FIERY_API int fiery_lift_point_indices(const fiery_lift_desc_t* desc, const float* calib_a, const float* calib_b,

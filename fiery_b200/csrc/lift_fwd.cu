@@ -18,7 +18,7 @@ namespace fiery {
 
 template <int DBLKS>
 __global__ void __launch_bounds__(64 * DBLKS, 2)
-lift_forward_kernel(const __grid_constant__ CUtensorMap head_map, const LiftParams P) {
+lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams P) {
     using TL = TileLayout<DBLKS>;
     constexpr int DPAD = TL::DPAD;
     constexpr int PS = TL::PS;
@@ -34,10 +34,11 @@ lift_forward_kernel(const __grid_constant__ CUtensorMap head_map, const LiftPara
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     if (tid == 0) {
-        tma_prefetch_desc(&head_map);
+        tma_prefetch_desc(&head_maps.depth);
+        tma_prefetch_desc(&head_maps.ctx);
         mbar_init(bar, 1);
         fence_mbar_init();
-        issue_tile_loads<DBLKS>(P, L, smem, &head_map, img, w0);
+        issue_tile_loads<DBLKS>(P, L, smem, &head_maps, img, w0);
     }
     stage_constants<DBLKS>(P, L, smem, img, w0);
     __syncthreads();
@@ -173,10 +174,10 @@ __global__ void compose_calibration_kernel(int n, const float* __restrict__ K, c
 // ---------------------------------------------------------------------------------------------------------------------
 // host launchers (called from c_api.cu)
 // ---------------------------------------------------------------------------------------------------------------------
-int encode_head_map(CUtensorMap* map, const void* head, int dtype, long long n_images, int head_channels, int hh, int ww);
+int encode_head_maps(HeadMaps* maps, const void* head, int dtype, const LiftParams& P);
 
 template <int DBLKS>
-static int launch_forward_t(const CUtensorMap& map, const LiftParams& P, cudaStream_t stream) {
+static int launch_forward_t(const HeadMaps& map, const LiftParams& P, cudaStream_t stream) {
     const TileLayout<DBLKS> L(P.hh, P.C);
     const int n_pblk = (L.PX + 31) / 32;
     FIERY_REQUIRE(n_pblk * (1 + P.C / 32) <= TileLayout<DBLKS>::NWARPS,
@@ -201,9 +202,8 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     FIERY_REQUIRE(P.C == 64, "channels=%d not supported by this build (C must be 64)", P.C);
     FIERY_REQUIRE(P.D >= 1 && P.D <= 48, "depth_bins=%d not supported by this build (1..48)", P.D);
     FIERY_REQUIRE(P.ww % 4 == 0, "feat_w=%d must be a multiple of 4 (TMA row pitch must be 16-byte aligned)", P.ww);
-    CUtensorMap map;
-    const long long n_images = static_cast<long long>(P.n_frames) * P.n_cameras;
-    int rc = encode_head_map(&map, head, head_dtype, n_images, P.head_channels, P.hh, P.ww);
+    HeadMaps map;
+    int rc = encode_head_maps(&map, head, head_dtype, P);
     if (rc != FIERY_OK) return rc;
     LiftParams Q = P;
     Q.accum = (P.bev_layout == FIERY_BEV_NHWC) ? bev_out : scratch;

@@ -148,21 +148,26 @@ __device__ __forceinline__ void stage_change_bits(const TileLayout<DBLKS>& L, un
     }
 }
 
-// ---- TMA issue: (D/8 + C/8) boxes of (4 cols, hh rows, 8 channels) ------------------------------------------------------
+// ---- TMA issue: DBLKS + C/8 boxes of (4 cols, hh rows, 8 channels, 1 image) ------------------------------------------------
+// Two 4-D views of the head tensor: `depth` covers channels [0, D) of every image, `ctx` channels [D, D+C).  Boxes that
+// stick out of a view (D not a multiple of 8, last column tile) are zero-filled on load and clipped on store.
+struct HeadMaps {
+    CUtensorMap depth;
+    CUtensorMap ctx;
+};
+
 template <int DBLKS>
 __device__ __forceinline__ void issue_tile_loads(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem,
-                                                 const CUtensorMap* map, int img, int w0) {
+                                                 const HeadMaps* maps, int img, int w0) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     const int box_bytes = CH_BOX * L.PX * 4;
     const int n_dbox = P.use_depth ? DBLKS : 0;
     const int n_cbox = L.C / CH_BOX;
     mbar_arrive_expect_tx(bar, static_cast<uint32_t>((n_dbox + n_cbox) * box_bytes));
-    const int ch_base = img * P.head_channels;
     for (int i = 0; i < n_dbox; ++i)
-        tma_load_3d(smem + L.off_prob + i * box_bytes, map, bar, w0, 0, ch_base + i * CH_BOX);
-    const int ctx0 = P.use_depth ? P.D : 0;
+        tma_load_4d(smem + L.off_prob + i * box_bytes, &maps->depth, bar, w0, 0, i * CH_BOX, img);
     for (int i = 0; i < n_cbox; ++i)
-        tma_load_3d(smem + L.off_ctx + i * box_bytes, map, bar, w0, 0, ch_base + ctx0 + i * CH_BOX);
+        tma_load_4d(smem + L.off_ctx + i * box_bytes, &maps->ctx, bar, w0, 0, i * CH_BOX, img);
 }
 
 // ---- phase 2: softmax over depth + in-place transposes ---------------------------------------------------------------

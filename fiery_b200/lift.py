@@ -249,9 +249,12 @@ class LiftSplat(nn.Module):
         desc = self._desc(c, B, n, head.dtype, mode, layout)
         grad_head = torch.empty_like(head)
         with torch.cuda.device(dev):
+            ws_bytes = int(lib.fiery_lift_workspace_bytes(desc))
+            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
             _lib.check(lib.fiery_lift_backward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
                                                c["v"].data_ptr(), c["d"].data_ptr(), g.data_ptr(), grad_head.data_ptr(),
-                                               _stream_ptr(dev)), "fiery_lift_backward")
+                                               ws.data_ptr() if ws is not None else 0, _stream_ptr(dev)),
+                       "fiery_lift_backward")
         return grad_head
 
 

@@ -98,13 +98,17 @@ FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head
                        const float* frustum_u, const float* frustum_v, const float* frustum_d,
                        float* bev_out, float* scratch, void* stream);
 
+/* Bytes of device workspace fiery_lift_backward needs when grad_bev is FIERY_BEV_NCHW (it is re-laid out channel-last
+ * there); 0 for NHWC.  Contents on entry/exit are irrelevant. */
+FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* desc);
+
 /*
  * Backward of the lift w.r.t. the head tensor.  grad_bev: (B',C,X,Y) fp32 in bev_layout; grad_head: same shape and
  * dtype as head, fully overwritten.  Calibration gets no gradient (geometry is integer, geometry.py:300).
  */
 FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                         const float* frustum_u, const float* frustum_v, const float* frustum_d,
-                        const float* grad_bev, void* grad_head, void* stream);
+                        const float* grad_bev, void* grad_head, float* workspace, void* stream);
 
 /*
  * Integer voxel coordinates of all N = n*D*h*w points per frame, in the reference's point order
