@@ -23,6 +23,13 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static encode_tiled_fn get_encode_fn() {
+    // cuTensorMapEncodeTiled is a driver call and needs a current context; a thread that has made no runtime call yet
+    // (e.g. the autograd engine's worker on its first backward) has none, so bind the primary context once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     static encode_tiled_fn fn = nullptr;
     if (fn) return fn;
     void* sym = nullptr;
@@ -101,7 +108,7 @@ static int make_params(const fiery_lift_desc_t* d, const float* calib_a, const f
     P.head_channels = d->channels + (P.use_depth ? d->depth_bins : 0);
     P.calib_mode = d->calib_mode;
     P.calib_a = calib_a; P.calib_b = calib_b; P.fu = fu; P.fv = fv; P.fd = fd;
-    P.accum = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr;
+    P.accum = nullptr; P.touched = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr;
     P.bev_layout = d->bev_layout;
     P.pillars = static_cast<long long>(d->bev_x) * d->bev_y;
     P.grid = make_grid_params(*d);
@@ -120,7 +127,8 @@ FIERY_API const char* fiery_last_error(void) { return g_last_error; }
 
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
     if (!d || d->bev_layout != FIERY_BEV_NCHW) return 0;
-    return static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y * d->channels * sizeof(float);
+    const size_t pillars = static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y;
+    return pillars * d->channels * sizeof(float) + ((pillars + 15) & ~static_cast<size_t>(15));   // accumulator + touched map
 }
 
 FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* d) {

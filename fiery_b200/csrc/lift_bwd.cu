@@ -50,11 +50,13 @@ lift_backward_kernel(const __grid_constant__ HeadMaps head_maps, const __grid_co
     }
     stage_constants<DBLKS>(P, L, smem, img, w0);
     __syncthreads();
+    if (tid == 64 * DBLKS - 1) stage_camera<DBLKS>(P, L, smem, img);     // overlaps the TMA latency
+    mbar_wait(bar, 0);
+    transform_tile<DBLKS>(P, L, smem);
     stage_pillars<DBLKS>(P, L, smem, w0);
     __syncthreads();
     stage_change_bits<DBLKS>(L, smem);
-    mbar_wait(bar, 0);
-    transform_tile<DBLKS>(P, L, smem);
+    __syncthreads();
 
     // ---- main loop ----------------------------------------------------------------------------------------------------
     float* s_prob = reinterpret_cast<float*>(smem + L.off_prob);
@@ -244,7 +246,7 @@ static int launch_backward_t(const HeadMaps& hm, const HeadMaps& gm, const LiftP
     const TileLayout<DBLKS> L(P.hh, P.C);
     const int n_pblk = (L.PX + 31) / 32;
     FIERY_REQUIRE(n_pblk * (1 + P.C / 32) <= TileLayout<DBLKS>::NWARPS, "feature map too tall for this build: h=%d", P.hh);
-    FIERY_REQUIRE((P.hh + DBLKS - 1) / DBLKS <= MAXR, "feature map too tall for this build: h=%d", P.hh);
+    FIERY_REQUIRE((P.hh + DBLKS - 1) / DBLKS <= MAXR && P.hh <= 32, "feature map too tall for this build: h=%d", P.hh);
     const int smem = L.total + L.PX * TileLayout<DBLKS>::DPAD * 4;
     FIERY_REQUIRE(smem <= 227 * 1024, "tile needs %d bytes of shared memory", smem);
     static bool configured = false;

@@ -16,6 +16,20 @@
 
 namespace fiery {
 
+// packed fp32x2 FMA (SASS FFMA2): d.lo += a * b.lo, d.hi += a * b.hi with the scalar a broadcast to both halves
+__device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, float a, unsigned long long b) {
+    unsigned long long aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(aa), "l"(b));
+}
+
+__device__ __forceinline__ void flush_pair(float* dst, unsigned long long lo, unsigned long long hi) {
+    float a, b, c, d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(lo));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(c), "=f"(d) : "l"(hi));
+    red_add_v4(dst, a, b, c, d);
+}
+
 template <int DBLKS>
 __global__ void __launch_bounds__(64 * DBLKS, 2)
 lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams P) {
@@ -41,92 +55,139 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
         issue_tile_loads<DBLKS>(P, L, smem, &head_maps, img, w0);
     }
     stage_constants<DBLKS>(P, L, smem, img, w0);
-    __syncthreads();
-    stage_pillars<DBLKS>(P, L, smem, w0);             // overlaps the TMA transfer
+    __syncthreads();                                  // mbarrier init + constants visible
+    // one lane composes R @ K^-1 while the TMA is in flight (its latency is longer than the composition); the result
+    // is first read after the barriers inside transform_tile
+    if (tid == 64 * DBLKS - 1) stage_camera<DBLKS>(P, L, smem, img);
+    mbar_wait(bar, 0);                                // head tile has landed
+    transform_tile<DBLKS>(P, L, smem);                // softmax + transposes (two barriers inside; camera visible after)
+    stage_pillars<DBLKS>(P, L, smem, w0);
     __syncthreads();
     stage_change_bits<DBLKS>(L, smem);
-    mbar_wait(bar, 0);                                // head tile has landed
-    transform_tile<DBLKS>(P, L, smem);                // softmax + transposes (two barriers inside)
+    __syncthreads();
 
     // ---- pooling: thread = (column wt, depth block dblk of 8, channel group cg of 4) ----------------------------------
     const int unit = warp * 2 + (lane >> 4);
     const int wt = unit / DBLKS, dblk = unit % DBLKS;
     const int cg = lane & 15;
-    const float* prob = reinterpret_cast<const float*>(smem + L.off_prob) + (wt * L.hh) * PS + dblk * 8;
-    const float* ctx = reinterpret_cast<const float*>(smem + L.off_ctx) + (wt * L.hh) * L.C + cg * 4;
-    const int* pillar = reinterpret_cast<const int*>(smem + L.off_pillar) + (wt * L.hh) * DPAD + dblk * 8;
-    const unsigned char* chg = smem + L.off_chg + (wt * L.hh) * DBLKS + dblk;
-    float* out = P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cg * 4;
-
-    float acc[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
-
     const int hh = L.hh;
-#pragma unroll 2
-    for (int h = 0; h < hh; ++h) {
-        const unsigned m = chg[h * DBLKS];
-        if (m) {   // some depth of this block enters a new pillar at row h: flush what was accumulated for the old one
+    const float* prob = reinterpret_cast<const float*>(smem + L.off_prob) + (wt * hh) * PS + dblk * 8;
+    const float* ctx = reinterpret_cast<const float*>(smem + L.off_ctx) + (wt * hh) * L.C + cg * 4;
+    const int* pillar = reinterpret_cast<const int*>(smem + L.off_pillar) + (wt * hh) * DPAD + dblk * 8;
+    const unsigned char* chg = smem + L.off_chg + (wt * hh) * DBLKS + dblk;
+    const unsigned brk = reinterpret_cast<const unsigned*>(smem + L.off_brk)[wt * DBLKS + dblk];
+    float* out = P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cg * 4;
+    unsigned char* flags = P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
+
+    unsigned long long acc[8][2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (m & (1u << j)) {
-                    const int pl = pillar[(h - 1) * DPAD + j];
-                    if (pl >= 0) red_add_v4(out + static_cast<size_t>(pl) * P.C, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                    acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0ull;
+
+    int h = 0;
+    while (true) {
+        // rows [h, h1) belong to one run for all 8 depths of this block
+        const unsigned rest = (h + 1 < 32) ? (brk >> (h + 1)) : 0u;
+        const int h1 = rest ? h + __ffs(rest) : hh;
+        const float* pp = prob + h * PS;
+        const float* cp = ctx + h * L.C;
+#pragma unroll 4
+        for (int r = h; r < h1; ++r, pp += PS, cp += L.C) {
+            const float4 p0 = *reinterpret_cast<const float4*>(pp);
+            const float4 p1 = *reinterpret_cast<const float4*>(pp + 4);
+            const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(cp);
+            // depth x context outer product (encoder.py:100), summed along the column
+            ffma2_bcast(acc[0][0], p0.x, c.x); ffma2_bcast(acc[0][1], p0.x, c.y);
+            ffma2_bcast(acc[1][0], p0.y, c.x); ffma2_bcast(acc[1][1], p0.y, c.y);
+            ffma2_bcast(acc[2][0], p0.z, c.x); ffma2_bcast(acc[2][1], p0.z, c.y);
+            ffma2_bcast(acc[3][0], p0.w, c.x); ffma2_bcast(acc[3][1], p0.w, c.y);
+            ffma2_bcast(acc[4][0], p1.x, c.x); ffma2_bcast(acc[4][1], p1.x, c.y);
+            ffma2_bcast(acc[5][0], p1.y, c.x); ffma2_bcast(acc[5][1], p1.y, c.y);
+            ffma2_bcast(acc[6][0], p1.z, c.x); ffma2_bcast(acc[6][1], p1.z, c.y);
+            ffma2_bcast(acc[7][0], p1.w, c.x); ffma2_bcast(acc[7][1], p1.w, c.y);
+        }
+        const bool last = h1 >= hh;
+        const unsigned m = last ? 0xffu : chg[h1 * DBLKS];     // depths whose run ends at row h1-1
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (m & (1u << j)) {
+                const int pl = pillar[(h1 - 1) * DPAD + j];
+                if (pl >= 0) {
+                    flush_pair(out + static_cast<size_t>(pl) * P.C, acc[j][0], acc[j][1]);
+                    if (flags && cg == 0) flags[pl] = 1;
                 }
             }
+            // clear the flushed accumulators with a mask (straight-line code: a conditional assignment here makes
+            // ptxas carry two copies of all 32 accumulator registers through the hot loop)
+            const unsigned long long keep = static_cast<unsigned long long>(static_cast<long long>(static_cast<int>((m >> j) & 1u) - 1));
+            acc[j][0] &= keep;
+            acc[j][1] &= keep;
         }
-        const float4 p0 = *reinterpret_cast<const float4*>(prob + h * PS);
-        const float4 p1 = *reinterpret_cast<const float4*>(prob + h * PS + 4);
-        const float4 c = *reinterpret_cast<const float4*>(ctx + h * L.C);
-        const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {   // depth x context outer product (encoder.py:100), summed along the column
-            acc[j][0] = fmaf(pv[j], c.x, acc[j][0]);
-            acc[j][1] = fmaf(pv[j], c.y, acc[j][1]);
-            acc[j][2] = fmaf(pv[j], c.z, acc[j][2]);
-            acc[j][3] = fmaf(pv[j], c.w, acc[j][3]);
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int pl = pillar[(hh - 1) * DPAD + j];
-        if (pl >= 0) red_add_v4(out + static_cast<size_t>(pl) * P.C, acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        if (last) break;
+        h = h1;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Finalize for NCHW output: accum (B', X*Y, C) -> bev (B', C, X*Y), and re-zero the accumulator so the next call can
-// reuse it (scratch invariant in include/fiery_b200.h).  32 pillars x 64 channels per block, coalesced on both sides.
+// Finalize for NCHW output: accum (B', X*Y, C) -> bev (B', C, X*Y).  Only ~1/3 of the pillars receive any point
+// (hard part 4), and the lift kernel marks those in a byte map, so untouched pillars are written
+// as zeros without reading the accumulator.  Touched accumulator rows and their flags are re-zeroed on the way, which
+// restores the scratch invariant of include/fiery_b200.h for the next call.
+// Block = 128 pillars x 64 channels: 16-byte loads (one pillar row per half-warp), shared tile [pillar][68] (conflict
+// free for both phases), then each lane writes 8 consecutive pillars of one channel as two 16-byte stores.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int FIN_PILLARS = 64;
+constexpr int FIN_PILLARS = 128;
+constexpr int FIN_STRIDE = 68;
 __global__ void __launch_bounds__(256)
-finalize_nchw_kernel(float* __restrict__ accum, float* __restrict__ bev, int C, long long pillars, int blocks_per_frame) {
-    __shared__ float tile[FIN_PILLARS][65];
+finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flags, float* __restrict__ bev,
+                     long long pillars, int blocks_per_frame) {
+    constexpr int C = 64;
+    __shared__ __align__(16) float tile[FIN_PILLARS * FIN_STRIDE];
+    __shared__ unsigned char sflag[FIN_PILLARS];
     const int frame = blockIdx.x / blocks_per_frame;
     const long long p0 = static_cast<long long>(blockIdx.x % blocks_per_frame) * FIN_PILLARS;
-    float* src = accum + (static_cast<size_t>(frame) * pillars + p0) * C;
-    const int tid = threadIdx.x;
     const int n_here = static_cast<int>(min(static_cast<long long>(FIN_PILLARS), pillars - p0));
-    // read: 16 lanes x float4 = one pillar row of 64 channels
-    for (int i = tid; i < FIN_PILLARS * 16; i += 256) {
+    const int tid = threadIdx.x;
+    unsigned char* f = flags + static_cast<size_t>(frame) * pillars + p0;
+    if (tid < FIN_PILLARS) {
+        unsigned char v = 0;
+        if (tid < n_here) {
+            v = f[tid];
+            if (v) f[tid] = 0;
+        }
+        sflag[tid] = v;
+    }
+    __syncthreads();
+    float* src = accum + (static_cast<size_t>(frame) * pillars + p0) * C;
+#pragma unroll
+    for (int it = 0; it < FIN_PILLARS * 16 / 256; ++it) {
+        const int i = it * 256 + tid;
         const int pl = i >> 4, q = i & 15;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pl < n_here) {
+        if (sflag[pl]) {
             float4* ptr = reinterpret_cast<float4*>(src + static_cast<size_t>(pl) * C) + q;
             v = *ptr;
             *ptr = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        tile[pl][q * 4 + 0] = v.x; tile[pl][q * 4 + 1] = v.y; tile[pl][q * 4 + 2] = v.z; tile[pl][q * 4 + 3] = v.w;
+        *reinterpret_cast<float4*>(tile + pl * FIN_STRIDE + q * 4) = v;
     }
     __syncthreads();
-    // write: each channel row gets FIN_PILLARS consecutive floats (256 B)
-    float* dst = bev + static_cast<size_t>(frame) * C * pillars + p0;
-    for (int i = tid; i < C * FIN_PILLARS; i += 256) {
-        const int c = i / FIN_PILLARS, pl = i % FIN_PILLARS;
-        if (pl < n_here) dst[static_cast<size_t>(c) * pillars + pl] = tile[pl][c];
+    const int c = tid & 63, grp = tid >> 6;
+    float* dst = bev + (static_cast<size_t>(frame) * C + c) * pillars + p0;
+    const bool vec_ok = (pillars & 3) == 0;
+#pragma unroll
+    for (int it = 0; it < FIN_PILLARS / 8 / 4; ++it) {
+        const int pl0 = (it * 4 + grp) * 8;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = tile[(pl0 + k) * FIN_STRIDE + c];
+        if (vec_ok && pl0 + 8 <= n_here) {
+            reinterpret_cast<float4*>(dst + pl0)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(dst + pl0)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (pl0 + k < n_here) dst[pl0 + k] = v[k];
+        }
     }
 }
 
@@ -180,6 +241,7 @@ template <int DBLKS>
 static int launch_forward_t(const HeadMaps& map, const LiftParams& P, cudaStream_t stream) {
     const TileLayout<DBLKS> L(P.hh, P.C);
     const int n_pblk = (L.PX + 31) / 32;
+    FIERY_REQUIRE(P.hh <= 32, "feat_h=%d not supported by this build (<= 32)", P.hh);
     FIERY_REQUIRE(n_pblk * (1 + P.C / 32) <= TileLayout<DBLKS>::NWARPS,
                   "feature map too tall for this build: h=%d needs %d staging warps, kernel has %d", P.hh,
                   n_pblk * (1 + P.C / 32), TileLayout<DBLKS>::NWARPS);
@@ -207,11 +269,15 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     if (rc != FIERY_OK) return rc;
     LiftParams Q = P;
     Q.accum = (P.bev_layout == FIERY_BEV_NHWC) ? bev_out : scratch;
+    // scratch = [accumulator floats][one "touched" byte per pillar]
+    Q.touched = (P.bev_layout == FIERY_BEV_NHWC)
+                    ? nullptr
+                    : reinterpret_cast<unsigned char*>(scratch + static_cast<size_t>(P.n_frames) * P.pillars * P.C);
     rc = launch_forward_t<6>(map, Q, stream);
     if (rc != FIERY_OK) return rc;
     if (P.bev_layout == FIERY_BEV_NCHW) {
         const int bpf = static_cast<int>((P.pillars + FIN_PILLARS - 1) / FIN_PILLARS);
-        finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * P.n_frames, 256, 0, stream>>>(scratch, bev_out, P.C, P.pillars, bpf);
+        finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * P.n_frames, 256, 0, stream>>>(scratch, Q.touched, bev_out, P.pillars, bpf);
         FIERY_CUDA_CHECK(cudaGetLastError());
     }
     return FIERY_OK;

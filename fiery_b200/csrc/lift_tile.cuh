@@ -31,6 +31,7 @@ struct LiftParams {
     const float* fv;         // (h) frustum pixel row coordinate      fiery.py:122
     const float* fd;         // (D) frustum depth                     fiery.py:115
     float* accum;            // forward: (B', X*Y, C) channel-last accumulation target
+    unsigned char* touched;  // forward, NCHW output: (B', X*Y) byte map of pillars that received a point
     const float* grad_bev;   // backward: (B', X*Y, C) or (B', C, X*Y)
     float* grad_head;        // backward output
     int bev_layout;
@@ -47,12 +48,13 @@ struct TileLayout {
 
     int hh, C, PX;                               // PX = hh * WT pixels per tile
     // byte offsets into dynamic shared memory
-    int off_bar, off_cam, off_u, off_v, off_d, off_prob, off_ctx, off_pillar, off_chg, total;
+    int off_bar, off_cam, off_brk, off_u, off_v, off_d, off_prob, off_ctx, off_pillar, off_chg, total;
 
     __host__ __device__ TileLayout(int hh_, int C_) : hh(hh_), C(C_), PX(hh_ * WT) {
         int o = 0;
         off_bar = o;    o += 16;
         off_cam = o;    o += 12 * 4;
+        off_brk = o;    o += WT * DBLKS * 4;     // per (column, depth block): bit h set <=> a pillar changes at row h
         off_u = o;      o += WT * 4;
         off_d = o;      o += DPAD * 4;
         off_v = o;      o += ((hh + 3) & ~3) * 4;
@@ -79,18 +81,55 @@ __device__ __forceinline__ void stage_constants(const LiftParams& P, const TileL
     if (tid < WT) s_u[tid] = (w0 + tid < P.ww) ? P.fu[w0 + tid] : 0.f;
     for (int i = tid; i < L.hh; i += blockDim.x) s_v[i] = P.fv[i];
     for (int i = tid; i < TileLayout<DBLKS>::DPAD; i += blockDim.x) s_d[i] = (i < P.D) ? P.fd[i] : 0.f;
-    if (tid == 32) {   // one lane of warp 1 composes R @ K^-1 while warp 0 issues the TMA
-        CameraTransform T;
-        load_camera(P.calib_mode, P.calib_a, P.calib_b, cam_flat, T);
-        float* s_cam = reinterpret_cast<float*>(smem + L.off_cam);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) s_cam[i] = T.m[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) s_cam[9 + i] = T.t[i];
-    }
+    unsigned* s_brk = reinterpret_cast<unsigned*>(smem + L.off_brk);
+    if (tid < WT * DBLKS) s_brk[tid] = 0u;
 }
 
-// ---- phase 1: pillar of every point of the tile (needs no head data; overlaps the TMA) --------------------------------
+// One lane composes R @ K^-1 (fiery.py:203) while the TMA is in flight and the other warps run the softmax.
+template <int DBLKS>
+__device__ __forceinline__ void stage_camera(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem, int cam_flat) {
+    CameraTransform T;
+    load_camera(P.calib_mode, P.calib_a, P.calib_b, cam_flat, T);
+    float* s_cam = reinterpret_cast<float*>(smem + L.off_cam);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) s_cam[i] = T.m[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s_cam[9 + i] = T.t[i];
+}
+
+// ---- pillar of every point of the tile -----------------------------------------------------------------------------------
+// Along an image column (fixed camera, column, depth) every fp32 operation of fiery.py:202-205,236 is monotone in the
+// row coordinate v (products with a constant, sums with a constant, division by a positive constant, truncation), so the
+// voxel coordinates (ix, iy) and the z class (below / inside / above the height slab) are monotone in the row index.
+// Rows with equal keys at both ends of an interval therefore share the key on the whole interval: the run structure of a
+// column is found by bisection with the *same* per-point arithmetic (bit-exact), evaluating ~2 points per run instead of
+// all h rows.
+struct PointKey {
+    int ix, iy, zc;     // ix in [-1, X], iy in [-1, Y] (clamped classes), zc: 0 below, 1 inside, 2 above
+};
+
+__device__ __forceinline__ PointKey point_key(const CameraTransform& T, const ColumnTerms& ct, const GridParams& g,
+                                              float v, float depth) {
+    float p[3];
+    ego_point(T, ct, v, depth, p);
+    const float sx = scaled_xy(g, 0, p[0]);
+    const float sy = scaled_xy(g, 1, p[1]);
+    const float az = __fsub_rn(p[2], g.off[2]);
+    PointKey k;
+    k.ix = (sx > -1.0f && sx < static_cast<float>(g.X)) ? static_cast<int>(sx) : (sx >= static_cast<float>(g.X) ? g.X : -1);
+    k.iy = (sy > -1.0f && sy < static_cast<float>(g.Y)) ? static_cast<int>(sy) : (sy >= static_cast<float>(g.Y) ? g.Y : -1);
+    k.zc = (az >= g.z_lo && az <= g.z_hi) ? 1 : (az > g.z_hi ? 2 : 0);
+    return k;
+}
+
+__device__ __forceinline__ bool same_key(const PointKey& a, const PointKey& b) {
+    return a.ix == b.ix && a.iy == b.iy && a.zc == b.zc;
+}
+
+__device__ __forceinline__ int key_pillar(const PointKey& k, const GridParams& g) {
+    return (k.ix >= 0 && k.ix < g.X && k.iy >= 0 && k.iy < g.Y && k.zc == 1) ? k.ix * g.Y + k.iy : -1;
+}
+
 template <int DBLKS>
 __device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem, int w0) {
     constexpr int DPAD = TileLayout<DBLKS>::DPAD;
@@ -110,18 +149,33 @@ __device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLay
         const int d = item % DPAD;
         const int wt = (item / DPAD) % WT;
         const int hs = item / (DPAD * WT);
-        const int h_lo = (L.hh * hs) / NHS, h_hi = (L.hh * (hs + 1)) / NHS;
+        const int h_lo = (L.hh * hs) / NHS, h_end = (L.hh * (hs + 1)) / NHS - 1;     // inclusive row range
         int* out = s_pillar + (wt * L.hh) * DPAD + d;
         if (d >= P.D || w0 + wt >= P.ww) {
-            for (int h = h_lo; h < h_hi; ++h) out[h * DPAD] = -1;
+            for (int h = h_lo; h <= h_end; ++h) out[h * DPAD] = -1;
             continue;
         }
         const float depth = s_d[d];
         const ColumnTerms ct = column_terms(T, s_u[wt], depth);
-        for (int h = h_lo; h < h_hi; ++h) {
-            float p[3];
-            ego_point(T, ct, s_v[h], depth, p);
-            out[h * DPAD] = pillar_of(g, p);
+        if (h_lo > h_end) continue;
+        const PointKey k_end = point_key(T, ct, g, s_v[h_end], depth);
+        int lo = h_lo;
+        PointKey k_lo = (h_lo == h_end) ? k_end : point_key(T, ct, g, s_v[h_lo], depth);
+        while (true) {
+            int e = h_end;                                   // last row of the run that starts at lo
+            if (!same_key(k_lo, k_end)) {
+                int a = lo, b = h_end;                       // key(a) == k_lo, key(b) != k_lo
+                while (b - a > 1) {
+                    const int m = (a + b) >> 1;
+                    if (same_key(point_key(T, ct, g, s_v[m], depth), k_lo)) a = m; else b = m;
+                }
+                e = a;
+            }
+            const int pl = key_pillar(k_lo, g);
+            for (int h = lo; h <= e; ++h) out[h * DPAD] = pl;
+            if (e >= h_end) break;
+            lo = e + 1;
+            k_lo = (lo == h_end) ? k_end : point_key(T, ct, g, s_v[lo], depth);
         }
     }
 }
@@ -132,6 +186,7 @@ __device__ __forceinline__ void stage_change_bits(const TileLayout<DBLKS>& L, un
     constexpr int DPAD = TileLayout<DBLKS>::DPAD;
     const int* s_pillar = reinterpret_cast<const int*>(smem + L.off_pillar);
     unsigned char* s_chg = smem + L.off_chg;
+    unsigned* s_brk = reinterpret_cast<unsigned*>(smem + L.off_brk);
     for (int item = threadIdx.x; item < L.PX * DBLKS; item += blockDim.x) {
         const int dblk = item % DBLKS;
         const int pix = item / DBLKS;               // col*hh + row
@@ -145,6 +200,7 @@ __device__ __forceinline__ void stage_change_bits(const TileLayout<DBLKS>& L, un
                 ((c1.x != p1.x) << 4) | ((c1.y != p1.y) << 5) | ((c1.z != p1.z) << 6) | ((c1.w != p1.w) << 7);
         }
         s_chg[item] = static_cast<unsigned char>(m);
+        if (m) atomicOr(s_brk + (pix / L.hh) * DBLKS + dblk, 1u << row);
     }
 }
 
@@ -210,9 +266,11 @@ __device__ __forceinline__ void transform_tile(const LiftParams& P, const TileLa
                 mx = fmaxf(mx, v[k]);
             }
             float sum = 0.f;
+            const float mx2 = mx * 1.4426950408889634f;
 #pragma unroll
             for (int k = 0; k < DPAD; ++k) {
-                v[k] = (v[k] == -INFINITY) ? 0.f : expf(v[k] - mx);          // encoder.py:99
+                // exp(x - max) as 2^(x*log2e - max*log2e): one FFMA + MUFU.EX2 (encoder.py:99); padding (-inf) gives 0
+                v[k] = exp2f(fmaf(v[k], 1.4426950408889634f, -mx2));
                 sum += v[k];
             }
             const float inv = __fdiv_rn(1.0f, sum);

