@@ -23,6 +23,12 @@ __device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, float a, un
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(aa), "l"(b));
 }
 
+// acc = 0 where `bit` is set, as predicated moves: straight-line code for the compiler (a C++ conditional assignment
+// makes ptxas keep two copies of all accumulator registers across the hot loop)
+__device__ __forceinline__ void clear_if(unsigned long long& a, unsigned long long& b, unsigned bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p mov.b64 %0, 0;\n\t@p mov.b64 %1, 0;\n\t}" : "+l"(a), "+l"(b) : "r"(bit));
+}
+
 __device__ __forceinline__ void flush_pair(float* dst, unsigned long long lo, unsigned long long hi) {
     float a, b, c, d;
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(lo));
@@ -75,9 +81,12 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
     const float* ctx = reinterpret_cast<const float*>(smem + L.off_ctx) + (wt * hh) * L.C + cg * 4;
     const int* pillar = reinterpret_cast<const int*>(smem + L.off_pillar) + (wt * hh) * DPAD + dblk * 8;
     const unsigned char* chg = smem + L.off_chg + (wt * hh) * DBLKS + dblk;
-    const unsigned brk = reinterpret_cast<const unsigned*>(smem + L.off_brk)[wt * DBLKS + dblk];
-    float* out = P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cg * 4;
-    unsigned char* flags = P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
+    // break rows of both half-warps (two depth blocks of one column) merged, so the warp walks the rows in lockstep;
+    // a break that belongs to the other half finds no change bit set here and flushes nothing
+    unsigned brk = reinterpret_cast<const unsigned*>(smem + L.off_brk)[wt * DBLKS + dblk];
+    brk |= __shfl_xor_sync(0xffffffffu, brk, 16);
+    char* out = reinterpret_cast<char*>(P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cg * 4);
+    unsigned char* flags = (P.touched && cg == 0) ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
 
     unsigned long long acc[8][2];
 #pragma unroll
@@ -85,7 +94,7 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
 
     int h = 0;
     while (true) {
-        // rows [h, h1) belong to one run for all 8 depths of this block
+        // rows [h, h1) belong to one run for all depths of this warp
         const unsigned rest = (h + 1 < 32) ? (brk >> (h + 1)) : 0u;
         const int h1 = rest ? h + __ffs(rest) : hh;
         const float* pp = prob + h * PS;
@@ -107,20 +116,21 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
         }
         const bool last = h1 >= hh;
         const unsigned m = last ? 0xffu : chg[h1 * DBLKS];     // depths whose run ends at row h1-1
+        if (m) {
+            const int* pl_row = pillar + (h1 - 1) * DPAD;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (m & (1u << j)) {
-                const int pl = pillar[(h1 - 1) * DPAD + j];
-                if (pl >= 0) {
-                    flush_pair(out + static_cast<size_t>(pl) * P.C, acc[j][0], acc[j][1]);
-                    if (flags && cg == 0) flags[pl] = 1;
+            for (int j = 0; j < 8; ++j) {
+                const unsigned bit = m & (1u << j);
+                if (bit) {
+                    const int pl = pl_row[j];
+                    if (pl >= 0) {
+                        flush_pair(reinterpret_cast<float*>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4)),
+                                   acc[j][0], acc[j][1]);
+                        if (flags) flags[pl] = 1;
+                    }
                 }
+                clear_if(acc[j][0], acc[j][1], bit);
             }
-            // clear the flushed accumulators with a mask (straight-line code: a conditional assignment here makes
-            // ptxas carry two copies of all 32 accumulator registers through the hot loop)
-            const unsigned long long keep = static_cast<unsigned long long>(static_cast<long long>(static_cast<int>((m >> j) & 1u) - 1));
-            acc[j][0] &= keep;
-            acc[j][1] &= keep;
         }
         if (last) break;
         h = h1;
@@ -128,66 +138,42 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Finalize for NCHW output: accum (B', X*Y, C) -> bev (B', C, X*Y).  Only ~1/3 of the pillars receive any point
-// (hard part 4), and the lift kernel marks those in a byte map, so untouched pillars are written
-// as zeros without reading the accumulator.  Touched accumulator rows and their flags are re-zeroed on the way, which
-// restores the scratch invariant of include/fiery_b200.h for the next call.
-// Block = 128 pillars x 64 channels: 16-byte loads (one pillar row per half-warp), shared tile [pillar][68] (conflict
-// free for both phases), then each lane writes 8 consecutive pillars of one channel as two 16-byte stores.
+// Finalize for NCHW output: accum (B', X*Y, C) -> bev (B', C, X*Y).  One thread per pillar: a lane reads its pillar's 256-byte
+// accumulator row as 16 independent 16-byte loads (its own two cache lines, so the sectors are fully used through L1),
+// and the warp then writes one channel of 32 consecutive pillars per store instruction -- a full 128-byte line.  No
+// shared-memory transpose (measured: the transposing variants are bound by 16-byte-per-lane scattered stores or by
+// bank conflicts, tools/microbench/finalize_variants.cu).  Only ~1/3-1/2 of the pillars receive any point, and the lift
+// kernel marks those in a byte map: unmarked pillars are written as zeros without touching the accumulator; marked
+// rows and their marks are re-zeroed on the way, which restores the scratch invariant of include/fiery_b200.h.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int FIN_PILLARS = 128;
-constexpr int FIN_STRIDE = 68;
-__global__ void __launch_bounds__(256)
+constexpr int FIN_THREADS = 256;
+__global__ void __launch_bounds__(FIN_THREADS)
 finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flags, float* __restrict__ bev,
                      long long pillars, int blocks_per_frame) {
     constexpr int C = 64;
-    __shared__ __align__(16) float tile[FIN_PILLARS * FIN_STRIDE];
-    __shared__ unsigned char sflag[FIN_PILLARS];
     const int frame = blockIdx.x / blocks_per_frame;
-    const long long p0 = static_cast<long long>(blockIdx.x % blocks_per_frame) * FIN_PILLARS;
-    const int n_here = static_cast<int>(min(static_cast<long long>(FIN_PILLARS), pillars - p0));
-    const int tid = threadIdx.x;
-    unsigned char* f = flags + static_cast<size_t>(frame) * pillars + p0;
-    if (tid < FIN_PILLARS) {
-        unsigned char v = 0;
-        if (tid < n_here) {
-            v = f[tid];
-            if (v) f[tid] = 0;
-        }
-        sflag[tid] = v;
+    const long long pl = static_cast<long long>(blockIdx.x % blocks_per_frame) * FIN_THREADS + threadIdx.x;
+    if (pl >= pillars) return;
+    unsigned char* f = flags + static_cast<size_t>(frame) * pillars + pl;
+    float4 v[C / 4];
+    if (*f) {
+        float4* row = reinterpret_cast<float4*>(accum + (static_cast<size_t>(frame) * pillars + pl) * C);
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) v[q] = row[q];
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        *f = 0;
+    } else {
+#pragma unroll
+        for (int q = 0; q < C / 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
-    float* src = accum + (static_cast<size_t>(frame) * pillars + p0) * C;
+    float* dst = bev + static_cast<size_t>(frame) * C * pillars + pl;
 #pragma unroll
-    for (int it = 0; it < FIN_PILLARS * 16 / 256; ++it) {
-        const int i = it * 256 + tid;
-        const int pl = i >> 4, q = i & 15;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sflag[pl]) {
-            float4* ptr = reinterpret_cast<float4*>(src + static_cast<size_t>(pl) * C) + q;
-            v = *ptr;
-            *ptr = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        *reinterpret_cast<float4*>(tile + pl * FIN_STRIDE + q * 4) = v;
-    }
-    __syncthreads();
-    const int c = tid & 63, grp = tid >> 6;
-    float* dst = bev + (static_cast<size_t>(frame) * C + c) * pillars + p0;
-    const bool vec_ok = (pillars & 3) == 0;
-#pragma unroll
-    for (int it = 0; it < FIN_PILLARS / 8 / 4; ++it) {
-        const int pl0 = (it * 4 + grp) * 8;
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = tile[(pl0 + k) * FIN_STRIDE + c];
-        if (vec_ok && pl0 + 8 <= n_here) {
-            reinterpret_cast<float4*>(dst + pl0)[0] = make_float4(v[0], v[1], v[2], v[3]);
-            reinterpret_cast<float4*>(dst + pl0)[1] = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (pl0 + k < n_here) dst[pl0 + k] = v[k];
-        }
+    for (int q = 0; q < C / 4; ++q) {
+        dst[static_cast<size_t>(4 * q + 0) * pillars] = v[q].x;
+        dst[static_cast<size_t>(4 * q + 1) * pillars] = v[q].y;
+        dst[static_cast<size_t>(4 * q + 2) * pillars] = v[q].z;
+        dst[static_cast<size_t>(4 * q + 3) * pillars] = v[q].w;
     }
 }
 
@@ -276,7 +262,7 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     rc = launch_forward_t<6>(map, Q, stream);
     if (rc != FIERY_OK) return rc;
     if (P.bev_layout == FIERY_BEV_NCHW) {
-        const int bpf = static_cast<int>((P.pillars + FIN_PILLARS - 1) / FIN_PILLARS);
+        const int bpf = static_cast<int>((P.pillars + FIN_THREADS - 1) / FIN_THREADS);
         finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * P.n_frames, 256, 0, stream>>>(scratch, Q.touched, bev_out, P.pillars, bpf);
         FIERY_CUDA_CHECK(cudaGetLastError());
     }

@@ -97,39 +97,7 @@ __device__ __forceinline__ void stage_camera(const LiftParams& P, const TileLayo
     for (int i = 0; i < 3; ++i) s_cam[9 + i] = T.t[i];
 }
 
-// ---- pillar of every point of the tile -----------------------------------------------------------------------------------
-// Along an image column (fixed camera, column, depth) every fp32 operation of fiery.py:202-205,236 is monotone in the
-// row coordinate v (products with a constant, sums with a constant, division by a positive constant, truncation), so the
-// voxel coordinates (ix, iy) and the z class (below / inside / above the height slab) are monotone in the row index.
-// Rows with equal keys at both ends of an interval therefore share the key on the whole interval: the run structure of a
-// column is found by bisection with the *same* per-point arithmetic (bit-exact), evaluating ~2 points per run instead of
-// all h rows.
-struct PointKey {
-    int ix, iy, zc;     // ix in [-1, X], iy in [-1, Y] (clamped classes), zc: 0 below, 1 inside, 2 above
-};
-
-__device__ __forceinline__ PointKey point_key(const CameraTransform& T, const ColumnTerms& ct, const GridParams& g,
-                                              float v, float depth) {
-    float p[3];
-    ego_point(T, ct, v, depth, p);
-    const float sx = scaled_xy(g, 0, p[0]);
-    const float sy = scaled_xy(g, 1, p[1]);
-    const float az = __fsub_rn(p[2], g.off[2]);
-    PointKey k;
-    k.ix = (sx > -1.0f && sx < static_cast<float>(g.X)) ? static_cast<int>(sx) : (sx >= static_cast<float>(g.X) ? g.X : -1);
-    k.iy = (sy > -1.0f && sy < static_cast<float>(g.Y)) ? static_cast<int>(sy) : (sy >= static_cast<float>(g.Y) ? g.Y : -1);
-    k.zc = (az >= g.z_lo && az <= g.z_hi) ? 1 : (az > g.z_hi ? 2 : 0);
-    return k;
-}
-
-__device__ __forceinline__ bool same_key(const PointKey& a, const PointKey& b) {
-    return a.ix == b.ix && a.iy == b.iy && a.zc == b.zc;
-}
-
-__device__ __forceinline__ int key_pillar(const PointKey& k, const GridParams& g) {
-    return (k.ix >= 0 && k.ix < g.X && k.iy >= 0 && k.iy < g.Y && k.zc == 1) ? k.ix * g.Y + k.iy : -1;
-}
-
+// ---- pillar (rank, fiery.py:236-256) of every point of the tile: WT x D x h evaluations of the reference arithmetic -------
 template <int DBLKS>
 __device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem, int w0) {
     constexpr int DPAD = TileLayout<DBLKS>::DPAD;
@@ -144,38 +112,24 @@ __device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLay
     for (int i = 0; i < 9; ++i) T.m[i] = s_cam[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) T.t[i] = s_cam[9 + i];
-    const GridParams& g = P.grid;
+    const GridParams g = P.grid;                            // registers, not constant-bank reloads in the loop
     for (int item = threadIdx.x; item < WT * DPAD * NHS; item += blockDim.x) {
         const int d = item % DPAD;
         const int wt = (item / DPAD) % WT;
         const int hs = item / (DPAD * WT);
-        const int h_lo = (L.hh * hs) / NHS, h_end = (L.hh * (hs + 1)) / NHS - 1;     // inclusive row range
-        int* out = s_pillar + (wt * L.hh) * DPAD + d;
+        const int h_lo = (L.hh * hs) / NHS, h_hi = (L.hh * (hs + 1)) / NHS;
+        int* out = s_pillar + (wt * L.hh + h_lo) * DPAD + d;
         if (d >= P.D || w0 + wt >= P.ww) {
-            for (int h = h_lo; h <= h_end; ++h) out[h * DPAD] = -1;
+            for (int h = h_lo; h < h_hi; ++h, out += DPAD) *out = -1;
             continue;
         }
         const float depth = s_d[d];
         const ColumnTerms ct = column_terms(T, s_u[wt], depth);
-        if (h_lo > h_end) continue;
-        const PointKey k_end = point_key(T, ct, g, s_v[h_end], depth);
-        int lo = h_lo;
-        PointKey k_lo = (h_lo == h_end) ? k_end : point_key(T, ct, g, s_v[h_lo], depth);
-        while (true) {
-            int e = h_end;                                   // last row of the run that starts at lo
-            if (!same_key(k_lo, k_end)) {
-                int a = lo, b = h_end;                       // key(a) == k_lo, key(b) != k_lo
-                while (b - a > 1) {
-                    const int m = (a + b) >> 1;
-                    if (same_key(point_key(T, ct, g, s_v[m], depth), k_lo)) a = m; else b = m;
-                }
-                e = a;
-            }
-            const int pl = key_pillar(k_lo, g);
-            for (int h = lo; h <= e; ++h) out[h * DPAD] = pl;
-            if (e >= h_end) break;
-            lo = e + 1;
-            k_lo = (lo == h_end) ? k_end : point_key(T, ct, g, s_v[lo], depth);
+#pragma unroll 2
+        for (int h = h_lo; h < h_hi; ++h, out += DPAD) {
+            float p[3];
+            ego_point(T, ct, s_v[h], depth, p);
+            *out = pillar_of(g, p);
         }
     }
 }

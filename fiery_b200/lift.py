@@ -201,6 +201,67 @@ class LiftSplat(nn.Module):
                                                      _stream_ptr(dev)), "fiery_compose_calibration")
         return comb, trans
 
+    # -- CUDA graph and host-buffer entry points ------------------------------------------------------------------------
+    def capture(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> "GraphedLift":
+        """Captures one forward lift of these (device-resident, static) tensors into a CUDA graph.  ``g = lift.capture(...)``;
+        ``bev = g()`` replays it: one graph launch instead of descriptor encoding + two kernel launches from Python.
+        The returned BEV tensor is the graph's static output buffer (overwritten by the next replay).  Inference only."""
+        return GraphedLift(self, head, intrinsics, extrinsics)
+
+    def lift_from_host(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
+                       out: Optional[torch.Tensor] = None, device: Optional[torch.device] = None,
+                       chunk_frames: int = 3) -> torch.Tensor:
+        """Host-buffer entry point: ``head`` (B'*n, D+C, h, w), ``intrinsics`` (B', n, 3, 3), ``extrinsics`` (B', n, 4, 4) in
+        (pinned) host memory -> BEV (B', C, X, Y) in pinned host memory.  Frames are independent, so the batch is cut into
+        chunks of ``chunk_frames`` and the three stages -- host->device copy, lift, device->host copy -- run on three
+        streams, overlapping the upload of chunk i+1 and the download of chunk i-1 with the lift of chunk i (PCIe is
+        full duplex).  Synchronises before returning.  Inference only."""
+        dev = device if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise _lib.FieryError("lift_from_host needs the module on a CUDA device: fiery_b200 has no CPU path")
+        c = self._constants(dev)
+        B, n = intrinsics.shape[:2]
+        C = self.encoder_out_channels
+        X, Y, _ = c["dim"]
+        if out is None:
+            out = torch.empty((B, C, X, Y), dtype=torch.float32).pin_memory()
+        st = self._host_streams(dev)
+        cur = torch.cuda.current_stream(dev)
+        for s in st:
+            s.wait_stream(cur)
+        up, run, down = st
+        prev_done = None
+        with torch.no_grad():
+            for f0 in range(0, B, max(1, chunk_frames)):
+                f1 = min(B, f0 + max(1, chunk_frames))
+                with torch.cuda.stream(up):
+                    h = head[f0 * n:f1 * n].to(dev, non_blocking=True)
+                    k = intrinsics[f0:f1].to(dev, non_blocking=True)
+                    e = extrinsics[f0:f1].to(dev, non_blocking=True)
+                    ready = torch.cuda.Event()
+                    ready.record(up)
+                with torch.cuda.stream(run):
+                    run.wait_event(ready)
+                    bev = self._launch_forward(h, k, e)
+                    for t in (h, k, e):
+                        t.record_stream(run)
+                    done = torch.cuda.Event()
+                    done.record(run)
+                with torch.cuda.stream(down):
+                    down.wait_event(done)
+                    out[f0:f1].copy_(bev, non_blocking=True)
+                    bev.record_stream(down)
+        cur.wait_stream(down)
+        down.synchronize()
+        return out
+
+    def _host_streams(self, dev):
+        key = (dev.index if dev.index is not None else torch.cuda.current_device())
+        cache = self.__dict__.setdefault("_streams", {})
+        if key not in cache:
+            cache[key] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        return cache[key]
+
     # -- raw launches (used by the autograd function and by bench.py) ------------------------------------------------
     def _launch_forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:
         _require_cuda(head, "head")
@@ -256,6 +317,29 @@ class LiftSplat(nn.Module):
                                                ws.data_ptr() if ws is not None else 0, _stream_ptr(dev)),
                        "fiery_lift_backward")
         return grad_head
+
+
+class GraphedLift:
+    """A captured forward lift (see ``LiftSplat.capture``)."""
+
+    def __init__(self, module: LiftSplat, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor):
+        _require_cuda(head, "head")
+        self.module, self.inputs = module, (head, intrinsics, extrinsics)
+        dev = head.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                       # warm-up outside capture: attribute setup, scratch allocation
+                module._launch_forward(head, intrinsics, extrinsics)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.output = module._launch_forward(head, intrinsics, extrinsics)
+
+    def __call__(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.output
 
 
 class _LiftSplatFunction(torch.autograd.Function):
