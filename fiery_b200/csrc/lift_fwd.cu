@@ -81,10 +81,6 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
     const float* ctx = reinterpret_cast<const float*>(smem + L.off_ctx) + (wt * hh) * L.C + cg * 4;
     const int* pillar = reinterpret_cast<const int*>(smem + L.off_pillar) + (wt * hh) * DPAD + dblk * 8;
     const unsigned char* chg = smem + L.off_chg + (wt * hh) * DBLKS + dblk;
-    // break rows of both half-warps (two depth blocks of one column) merged, so the warp walks the rows in lockstep;
-    // a break that belongs to the other half finds no change bit set here and flushes nothing
-    unsigned brk = reinterpret_cast<const unsigned*>(smem + L.off_brk)[wt * DBLKS + dblk];
-    brk |= __shfl_xor_sync(0xffffffffu, brk, 16);
     char* out = reinterpret_cast<char*>(P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cg * 4);
     unsigned char* flags = (P.touched && cg == 0) ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
 
@@ -92,48 +88,50 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0ull;
 
-    int h = 0;
-    while (true) {
-        // rows [h, h1) belong to one run for all depths of this warp
-        const unsigned rest = (h + 1 < 32) ? (brk >> (h + 1)) : 0u;
-        const int h1 = rest ? h + __ffs(rest) : hh;
-        const float* pp = prob + h * PS;
-        const float* cp = ctx + h * L.C;
-#pragma unroll 4
-        for (int r = h; r < h1; ++r, pp += PS, cp += L.C) {
-            const float4 p0 = *reinterpret_cast<const float4*>(pp);
-            const float4 p1 = *reinterpret_cast<const float4*>(pp + 4);
-            const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(cp);
-            // depth x context outer product (encoder.py:100), summed along the column
-            ffma2_bcast(acc[0][0], p0.x, c.x); ffma2_bcast(acc[0][1], p0.x, c.y);
-            ffma2_bcast(acc[1][0], p0.y, c.x); ffma2_bcast(acc[1][1], p0.y, c.y);
-            ffma2_bcast(acc[2][0], p0.z, c.x); ffma2_bcast(acc[2][1], p0.z, c.y);
-            ffma2_bcast(acc[3][0], p0.w, c.x); ffma2_bcast(acc[3][1], p0.w, c.y);
-            ffma2_bcast(acc[4][0], p1.x, c.x); ffma2_bcast(acc[4][1], p1.x, c.y);
-            ffma2_bcast(acc[5][0], p1.y, c.x); ffma2_bcast(acc[5][1], p1.y, c.y);
-            ffma2_bcast(acc[6][0], p1.z, c.x); ffma2_bcast(acc[6][1], p1.z, c.y);
-            ffma2_bcast(acc[7][0], p1.w, c.x); ffma2_bcast(acc[7][1], p1.w, c.y);
-        }
-        const bool last = h1 >= hh;
-        const unsigned m = last ? 0xffu : chg[h1 * DBLKS];     // depths whose run ends at row h1-1
+    // Rows in lockstep.  Pillar changes are frequent at warp level (16 depths share a warp: ~11 of 28 rows see a change
+    // somewhere with a 1-degree camera roll), so the per-row cost of looking is kept to one byte load and a branch.
+    const float* pp = prob;
+    const float* cp = ctx;
+    const unsigned char* mp = chg;
+    const int* plp = pillar - DPAD;                  // row h-1
+#pragma unroll 2
+    for (int h = 0; h < hh; ++h, pp += PS, cp += L.C, mp += DBLKS, plp += DPAD) {
+        const unsigned m = *mp;                       // depths of this block whose pillar differs from row h-1 (0 at h = 0)
         if (m) {
-            const int* pl_row = pillar + (h1 - 1) * DPAD;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const unsigned bit = m & (1u << j);
-                if (bit) {
-                    const int pl = pl_row[j];
+                const unsigned ended = m & (1u << j);
+                if (ended) {
+                    const int pl = plp[j];
                     if (pl >= 0) {
                         flush_pair(reinterpret_cast<float*>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4)),
                                    acc[j][0], acc[j][1]);
                         if (flags) flags[pl] = 1;
                     }
                 }
-                clear_if(acc[j][0], acc[j][1], bit);
+                clear_if(acc[j][0], acc[j][1], ended);     // predicated in-place reset (see clear_if)
             }
         }
-        if (last) break;
-        h = h1;
+        const float4 p0 = *reinterpret_cast<const float4*>(pp);
+        const float4 p1 = *reinterpret_cast<const float4*>(pp + 4);
+        const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(cp);
+        // depth x context outer product (encoder.py:100), summed along the column
+        ffma2_bcast(acc[0][0], p0.x, c.x); ffma2_bcast(acc[0][1], p0.x, c.y);
+        ffma2_bcast(acc[1][0], p0.y, c.x); ffma2_bcast(acc[1][1], p0.y, c.y);
+        ffma2_bcast(acc[2][0], p0.z, c.x); ffma2_bcast(acc[2][1], p0.z, c.y);
+        ffma2_bcast(acc[3][0], p0.w, c.x); ffma2_bcast(acc[3][1], p0.w, c.y);
+        ffma2_bcast(acc[4][0], p1.x, c.x); ffma2_bcast(acc[4][1], p1.x, c.y);
+        ffma2_bcast(acc[5][0], p1.y, c.x); ffma2_bcast(acc[5][1], p1.y, c.y);
+        ffma2_bcast(acc[6][0], p1.z, c.x); ffma2_bcast(acc[6][1], p1.z, c.y);
+        ffma2_bcast(acc[7][0], p1.w, c.x); ffma2_bcast(acc[7][1], p1.w, c.y);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int pl = plp[j];                        // plp now points at the last row
+        if (pl >= 0) {
+            flush_pair(reinterpret_cast<float*>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4)), acc[j][0], acc[j][1]);
+            if (flags) flags[pl] = 1;
+        }
     }
 }
 

@@ -263,7 +263,8 @@ class LiftSplat(nn.Module):
         return cache[key]
 
     # -- raw launches (used by the autograd function and by bench.py) ------------------------------------------------
-    def _launch_forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:
+    def _launch_forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
+                        scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
         _require_cuda(head, "head")
         lib = _lib.load()
         dev = head.device
@@ -287,7 +288,9 @@ class LiftSplat(nn.Module):
                 desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NCHW)
                 store = torch.empty((B, C, X, Y), dtype=torch.float32, device=dev)
                 out = store
-                scratch_ptr = _scratch.get(dev, int(lib.fiery_lift_scratch_bytes(desc))).data_ptr() if B else 0
+                if scratch is None and B:
+                    scratch = _scratch.get(dev, int(lib.fiery_lift_scratch_bytes(desc)))
+                scratch_ptr = scratch.data_ptr() if B else 0
             _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
                                               c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
                                               _stream_ptr(dev)), "fiery_lift_forward")
@@ -332,10 +335,17 @@ class GraphedLift:
             for _ in range(2):                       # warm-up outside capture: attribute setup, scratch allocation
                 module._launch_forward(head, intrinsics, extrinsics)
         torch.cuda.current_stream(dev).wait_stream(side)
+        # the graph owns its accumulation scratch (zeroed once here; every replay leaves it zeroed again)
+        c = module._constants(dev)
+        B, n = intrinsics.shape[:2]
+        self.scratch = None
+        if module.output_layout != "channels_last" and B:
+            desc = module._desc(c, B, n, head.dtype, _lib.CALIB_RAW, _lib.BEV_NCHW)
+            self.scratch = torch.zeros(int(_lib.load().fiery_lift_scratch_bytes(desc)) // 4, dtype=torch.float32, device=dev)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
-            self.output = module._launch_forward(head, intrinsics, extrinsics)
+            self.output = module._launch_forward(head, intrinsics, extrinsics, scratch=self.scratch)
 
     def __call__(self) -> torch.Tensor:
         self.graph.replay()
