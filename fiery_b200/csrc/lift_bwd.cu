@@ -249,10 +249,10 @@ static int launch_backward_t(const HeadMaps& hm, const HeadMaps& gm, const LiftP
     FIERY_REQUIRE((P.hh + DBLKS - 1) / DBLKS <= MAXR && P.hh <= 32, "feature map too tall for this build: h=%d", P.hh);
     const int smem = L.total + L.PX * TileLayout<DBLKS>::DPAD * 4;
     FIERY_REQUIRE(smem <= 227 * 1024, "tile needs %d bytes of shared memory", smem);
-    static bool configured = false;
-    if (!configured) {
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_backward_kernel<DBLKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+    static int smem_configured = 0;
+    if (smem > smem_configured) {
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_backward_kernel<DBLKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_configured = smem;
     }
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
     lift_backward_kernel<DBLKS><<<static_cast<unsigned>(n_tiles), 64 * DBLKS, smem, stream>>>(hm, gm, P);

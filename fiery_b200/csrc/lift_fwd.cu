@@ -304,10 +304,10 @@ static int launch_forward_t(const HeadMaps& map, LiftParams P, cudaStream_t stre
     FIERY_REQUIRE(n_pblk * (1 + P.C / 32) <= TileLayout<DBLKS>::NWARPS,
                   "feature map too tall for this build: h=%d needs %d staging warps, kernel has %d", P.hh,
                   n_pblk * (1 + P.C / 32), TileLayout<DBLKS>::NWARPS);
-    static int blocks_per_sm = 0, n_sm = 0;
-    if (!blocks_per_sm) {
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_kernel<DBLKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              227 * 1024));
+    static int blocks_per_sm = 0, n_sm = 0, smem_configured = 0;
+    if (L.total > smem_configured) {       // opt in to > 48 KB of dynamic shared memory (the kernel also has a little static)
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_kernel<DBLKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        smem_configured = L.total;
         int dev = 0;
         FIERY_CUDA_CHECK(cudaGetDevice(&dev));
         FIERY_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
