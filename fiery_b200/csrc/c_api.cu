@@ -78,7 +78,6 @@ int encode_head_maps(HeadMaps* maps, const void* head, int dtype, const LiftPara
 
 // launchers defined next to their kernels
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch, cudaStream_t);
-size_t lift_queue_bytes(int n_frames);
 int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, float* workspace, cudaStream_t);
 int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t);
 int launch_compose(int n, const float* K, const float* E, float* combined, float* translation, cudaStream_t);
@@ -109,8 +108,7 @@ static int make_params(const fiery_lift_desc_t* d, const float* calib_a, const f
     P.head_channels = d->channels + (P.use_depth ? d->depth_bins : 0);
     P.calib_mode = d->calib_mode;
     P.calib_a = calib_a; P.calib_b = calib_b; P.fu = fu; P.fv = fv; P.fd = fd;
-    P.accum = nullptr; P.touched = nullptr; P.bev = nullptr; P.queue = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr;
-    P.n_items = P.tiles_per_frame = P.fin_chunks_per_frame = P.fin_lag = 0;
+    P.accum = nullptr; P.touched = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr;
     P.bev_layout = d->bev_layout;
     P.pillars = static_cast<long long>(d->bev_x) * d->bev_y;
     P.grid = make_grid_params(*d);
@@ -128,13 +126,9 @@ FIERY_API int fiery_abi_version(void) { return FIERY_B200_ABI_VERSION; }
 FIERY_API const char* fiery_last_error(void) { return g_last_error; }
 
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
-    if (!d) return 0;
-    size_t bytes = lift_queue_bytes(d->n_frames);                                                  // work queue counters
-    if (d->bev_layout == FIERY_BEV_NCHW) {
-        const size_t pillars = static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y;
-        bytes += pillars * d->channels * sizeof(float) + ((pillars + 15) & ~static_cast<size_t>(15));   // accumulator + touched map
-    }
-    return bytes;
+    if (!d || d->bev_layout != FIERY_BEV_NCHW) return 0;
+    const size_t pillars = static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y;
+    return pillars * d->channels * sizeof(float) + ((pillars + 15) & ~static_cast<size_t>(15));   // accumulator + touched map
 }
 
 FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* d) {
@@ -150,8 +144,7 @@ FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head
     if (rc != FIERY_OK) return rc;
     if (P.n_frames == 0) return FIERY_OK;
     FIERY_REQUIRE(head && bev_out, "head / bev_out is NULL");
-    FIERY_REQUIRE(scratch != nullptr, "scratch is NULL (fiery_lift_scratch_bytes() zeroed bytes are required)");
-    FIERY_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "scratch must be 256-byte aligned");
+    FIERY_REQUIRE(desc->bev_layout == FIERY_BEV_NHWC || scratch != nullptr, "NCHW output needs the zeroed scratch buffer");
     return launch_lift_forward(P, head, desc->head_dtype, bev_out, scratch, static_cast<cudaStream_t>(stream));
 }
 

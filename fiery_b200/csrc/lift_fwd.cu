@@ -36,26 +36,36 @@ __device__ __forceinline__ void flush_pair(float* dst, unsigned long long lo, un
     red_add_v4(dst, a, b, c, d);
 }
 
-// One tile of the forward lift (see the file header): TMA -> softmax/transposes -> pillar ranks -> pooling.
 template <int DBLKS>
-__device__ __forceinline__ void run_tile(const HeadMaps& head_maps, const LiftParams& P, const TileLayout<DBLKS>& L,
-                                         unsigned char* smem, uint64_t* bar, unsigned parity, int frame, int tile_in_frame) {
+__global__ void __launch_bounds__(64 * DBLKS, 2)
+lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams P) {
     using TL = TileLayout<DBLKS>;
     constexpr int DPAD = TL::DPAD;
     constexpr int PS = TL::PS;
-    // tile = (frame, camera, 4-column group): tile_in_frame = camera * n_wtiles + wtile
-    const int wtile = tile_in_frame % P.n_wtiles;
-    const int img = frame * P.n_cameras + tile_in_frame / P.n_wtiles;          // flat (frame, camera)
+    extern __shared__ __align__(128) unsigned char smem[];
+    const TL L(P.hh, P.C);
+
+    // tile coordinates: blockIdx.x = (frame*n + camera) * n_wtiles + wtile
+    const int wtile = blockIdx.x % P.n_wtiles;
+    const int img = blockIdx.x / P.n_wtiles;          // flat (frame, camera)
+    const int frame = img / P.n_cameras;
     const int w0 = wtile * WT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    if (tid == 0) issue_tile_loads<DBLKS>(P, L, smem, &head_maps, img, w0);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    if (tid == 0) {
+        tma_prefetch_desc(&head_maps.depth);
+        tma_prefetch_desc(&head_maps.ctx);
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        issue_tile_loads<DBLKS>(P, L, smem, &head_maps, img, w0);
+    }
     stage_constants<DBLKS>(P, L, smem, img, w0);
     __syncthreads();                                  // mbarrier init + constants visible
     // one lane composes R @ K^-1 while the TMA is in flight (its latency is longer than the composition); the result
     // is first read after the barriers inside transform_tile
     if (tid == 64 * DBLKS - 1) stage_camera<DBLKS>(P, L, smem, img);
-    mbar_wait(bar, parity);                           // head tile has landed
+    mbar_wait(bar, 0);                                // head tile has landed
     transform_tile<DBLKS>(P, L, smem);                // softmax + transposes (two barriers inside; camera visible after)
     stage_pillars<DBLKS>(P, L, smem, w0);
     __syncthreads();
@@ -126,125 +136,42 @@ __device__ __forceinline__ void run_tile(const HeadMaps& head_maps, const LiftPa
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// One work item of the fused kernel: the NCHW finalize of 64*DBLKS pillars of one frame (thread per pillar).
-// accum (X*Y, C) -> bev (C, X*Y); see finalize_pillar below.
+// Finalize for NCHW output: accum (B', X*Y, C) -> bev (B', C, X*Y).  One thread per pillar: a lane reads its pillar's 256-byte
+// accumulator row as 16 independent 16-byte loads (its own two cache lines, so the sectors are fully used through L1),
+// and the warp then writes one channel of 32 consecutive pillars per store instruction -- a full 128-byte line.  No
+// shared-memory transpose (measured: the transposing variants are bound by 16-byte-per-lane scattered stores or by
+// bank conflicts, tools/microbench/finalize_variants.cu).  Only ~1/3-1/2 of the pillars receive any point, and the lift
+// kernel marks those in a byte map: unmarked pillars are written as zeros without touching the accumulator; marked
+// rows and their marks are re-zeroed on the way, which restores the scratch invariant of include/fiery_b200.h.
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void finalize_pillar(float* __restrict__ accum_frame, unsigned char* __restrict__ flags_frame,
-                                                float* __restrict__ bev_frame, long long pillars, long long pl) {
-    constexpr int C = 64, HALF = C / 8;     // two passes of 32 channels keep this path inside the tile path's register budget
+constexpr int FIN_THREADS = 256;
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flags, float* __restrict__ bev,
+                     long long pillars, int blocks_per_frame) {
+    constexpr int C = 64;
+    const int frame = blockIdx.x / blocks_per_frame;
+    const long long pl = static_cast<long long>(blockIdx.x % blocks_per_frame) * FIN_THREADS + threadIdx.x;
     if (pl >= pillars) return;
-    const bool touched = __ldcg(flags_frame + pl) != 0;
-    float4* row = reinterpret_cast<float4*>(accum_frame + pl * C);
-    float* dst = bev_frame + pl;
+    unsigned char* f = flags + static_cast<size_t>(frame) * pillars + pl;
+    float4 v[C / 4];
+    if (*f) {
+        float4* row = reinterpret_cast<float4*>(accum + (static_cast<size_t>(frame) * pillars + pl) * C);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        float4 v[HALF];
-        if (touched) {
+        for (int q = 0; q < C / 4; ++q) v[q] = row[q];
 #pragma unroll
-            for (int q = 0; q < HALF; ++q) v[q] = __ldcg(row + half * HALF + q);   // L2 only: written by reductions, read once
+        for (int q = 0; q < C / 4; ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        *f = 0;
+    } else {
 #pragma unroll
-            for (int q = 0; q < HALF; ++q) row[half * HALF + q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-#pragma unroll
-            for (int q = 0; q < HALF; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int q = 0; q < HALF; ++q) {
-            const int c = 4 * (half * HALF + q);
-            dst[static_cast<size_t>(c + 0) * pillars] = v[q].x;
-            dst[static_cast<size_t>(c + 1) * pillars] = v[q].y;
-            dst[static_cast<size_t>(c + 2) * pillars] = v[q].z;
-            dst[static_cast<size_t>(c + 3) * pillars] = v[q].w;
-        }
+        for (int q = 0; q < C / 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (touched) flags_frame[pl] = 0;
-}
-
-// Work queue of the fused forward kernel.  Items are claimed in order with one atomicAdd per item:
-//   tiles(0) ... tiles(LAG-1), then for f >= LAG: tiles(f) followed by finalize(f-LAG), then the remaining finalizes.
-// A finalize item waits (acquire) until all tiles of its frame have published their reductions; the lag makes that
-// wait a formality.  Finalize items are DRAM-bound, tile items issue-bound: interleaving them on one SM overlaps the two.
-struct WorkItem {
-    int is_tile, frame, index;
-};
-
-__device__ __forceinline__ WorkItem decode_item(const LiftParams& P, int i) {
-    const int T = P.tiles_per_frame, Cn = P.fin_chunks_per_frame, F = P.n_frames;
-    const int lag = min(P.fin_lag, F);
-    WorkItem w;
-    if (Cn == 0) { w.is_tile = 1; w.frame = i / T; w.index = i % T; return w; }
-    if (i < lag * T) { w.is_tile = 1; w.frame = i / T; w.index = i % T; return w; }
-    i -= lag * T;
-    const int mid = (F - lag) * (T + Cn);
-    if (i < mid) {
-        const int blk = i / (T + Cn), r = i % (T + Cn);
-        if (r < T) { w.is_tile = 1; w.frame = lag + blk; w.index = r; }
-        else { w.is_tile = 0; w.frame = blk; w.index = r - T; }
-        return w;
-    }
-    i -= mid;
-    w.is_tile = 0; w.frame = (F - lag) + i / Cn; w.index = i % Cn;
-    return w;
-}
-
-template <int DBLKS>
-__global__ void __launch_bounds__(64 * DBLKS, 2)
-lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams P) {
-    using TL = TileLayout<DBLKS>;
-    constexpr int DPAD = TL::DPAD;
-    constexpr int PS = TL::PS;
-    constexpr int NT = 64 * DBLKS;
-    extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ int s_item;
-    const TL L(P.hh, P.C);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    int* q_head = P.queue;                  // [0] next item, [1] CTAs that have finished, [2 + f] finished tiles of frame f
-    int* q_done = P.queue + 2;
-    if (tid == 0) {
-        tma_prefetch_desc(&head_maps.depth);
-        tma_prefetch_desc(&head_maps.ctx);
-        mbar_init(bar, 1);
-        fence_mbar_init();
-    }
-    unsigned tiles_done = 0;                // parity of the mbarrier phase
-
-    while (true) {
-        __syncthreads();                    // previous item fully consumed (shared memory, s_item)
-        if (tid == 0) s_item = atomicAdd(q_head, 1);
-        __syncthreads();
-        const int item = s_item;
-        if (item >= P.n_items) break;
-        const WorkItem w = decode_item(P, item);
-        if (!w.is_tile) {
-            if (tid == 0) {
-                const volatile int* done = q_done + w.frame;
-                while (*done < P.tiles_per_frame) __nanosleep(200);
-                __threadfence();
-            }
-            __syncthreads();
-            const size_t fo = static_cast<size_t>(w.frame) * P.pillars;
-            finalize_pillar(P.accum + fo * P.C, P.touched + fo, P.bev + fo * P.C, P.pillars,
-                            static_cast<long long>(w.index) * NT + tid);
-            continue;
-        }
-        run_tile<DBLKS>(head_maps, P, L, smem, bar, tiles_done & 1u, w.frame, w.index);
-        ++tiles_done;
-        __syncthreads();                    // all reductions of this tile issued
-        if (tid == 0) {
-            __threadfence();                // ... and visible before the frame counter moves
-            atomicAdd(q_done + w.frame, 1);
-        }
-    }
-    // the last CTA to leave resets the queue for the next launch (part of the scratch invariant)
-    if (tid == 0) {
-        __threadfence();
-        if (atomicAdd(q_head + 1, 1) == static_cast<int>(gridDim.x) - 1) {
-            for (int f = 0; f < P.n_frames; ++f) q_done[f] = 0;
-            q_head[1] = 0;
-            __threadfence();
-            q_head[0] = 0;
-        }
+    float* dst = bev + static_cast<size_t>(frame) * C * pillars + pl;
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) {
+        dst[static_cast<size_t>(4 * q + 0) * pillars] = v[q].x;
+        dst[static_cast<size_t>(4 * q + 1) * pillars] = v[q].y;
+        dst[static_cast<size_t>(4 * q + 2) * pillars] = v[q].z;
+        dst[static_cast<size_t>(4 * q + 3) * pillars] = v[q].w;
     }
 }
 
@@ -294,43 +221,26 @@ __global__ void compose_calibration_kernel(int n, const float* __restrict__ K, c
 // ---------------------------------------------------------------------------------------------------------------------
 int encode_head_maps(HeadMaps* maps, const void* head, int dtype, const LiftParams& P);
 
-constexpr int FIN_LAG = 4;   // finalize of frame f is queued after the tiles of frame f + FIN_LAG
-
 template <int DBLKS>
-static int launch_forward_t(const HeadMaps& map, LiftParams P, cudaStream_t stream) {
+static int launch_forward_t(const HeadMaps& map, const LiftParams& P, cudaStream_t stream) {
     const TileLayout<DBLKS> L(P.hh, P.C);
     const int n_pblk = (L.PX + 31) / 32;
     FIERY_REQUIRE(P.hh <= 32, "feat_h=%d not supported by this build (<= 32)", P.hh);
     FIERY_REQUIRE(n_pblk * (1 + P.C / 32) <= TileLayout<DBLKS>::NWARPS,
                   "feature map too tall for this build: h=%d needs %d staging warps, kernel has %d", P.hh,
                   n_pblk * (1 + P.C / 32), TileLayout<DBLKS>::NWARPS);
-    static int blocks_per_sm = 0, n_sm = 0, smem_configured = 0;
-    if (L.total > smem_configured) {       // opt in to > 48 KB of dynamic shared memory (the kernel also has a little static)
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_kernel<DBLKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        smem_configured = L.total;
-        int dev = 0;
-        FIERY_CUDA_CHECK(cudaGetDevice(&dev));
-        FIERY_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        FIERY_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, lift_forward_kernel<DBLKS>, 64 * DBLKS, L.total));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    static bool configured = false;
+    if (!configured) {
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_kernel<DBLKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              227 * 1024));
+        configured = true;
     }
     FIERY_REQUIRE(L.total <= 227 * 1024, "tile needs %d bytes of shared memory", L.total);
-    P.tiles_per_frame = P.n_cameras * P.n_wtiles;
-    P.fin_chunks_per_frame = (P.bev_layout == FIERY_BEV_NCHW) ? static_cast<int>((P.pillars + 64 * DBLKS - 1) / (64 * DBLKS)) : 0;
-    P.fin_lag = FIN_LAG;
-    const long long n_items = static_cast<long long>(P.n_frames) * (P.tiles_per_frame + P.fin_chunks_per_frame);
-    FIERY_REQUIRE(n_items < (1ll << 31), "too many work items");
-    P.n_items = static_cast<int>(n_items);
-    // persistent grid: every resident CTA pulls items from the queue (all CTAs must be co-resident: a finalize item may
-    // wait for tiles that other CTAs are still running)
-    const int grid = static_cast<int>(n_items < static_cast<long long>(blocks_per_sm) * n_sm ? n_items : static_cast<long long>(blocks_per_sm) * n_sm);
-    lift_forward_kernel<DBLKS><<<grid, 64 * DBLKS, L.total, stream>>>(map, P);
+    const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
+    lift_forward_kernel<DBLKS><<<static_cast<unsigned>(n_tiles), 64 * DBLKS, L.total, stream>>>(map, P);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }
-
-// scratch layout: [work queue: 2 + n_frames ints, padded to 256 B][accumulator floats (NCHW only)][touched bytes (NCHW only)]
-size_t lift_queue_bytes(int n_frames) { return (static_cast<size_t>(2 + n_frames) * 4 + 255) & ~static_cast<size_t>(255); }
 
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch,
                         cudaStream_t stream) {
@@ -342,17 +252,19 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     int rc = encode_head_maps(&map, head, head_dtype, P);
     if (rc != FIERY_OK) return rc;
     LiftParams Q = P;
-    char* base = reinterpret_cast<char*>(scratch);
-    Q.queue = reinterpret_cast<int*>(base);
-    Q.bev = bev_out;
-    if (P.bev_layout == FIERY_BEV_NHWC) {
-        Q.accum = bev_out;
-        Q.touched = nullptr;
-    } else {
-        Q.accum = reinterpret_cast<float*>(base + lift_queue_bytes(P.n_frames));
-        Q.touched = reinterpret_cast<unsigned char*>(Q.accum + static_cast<size_t>(P.n_frames) * P.pillars * P.C);
+    Q.accum = (P.bev_layout == FIERY_BEV_NHWC) ? bev_out : scratch;
+    // scratch = [accumulator floats][one "touched" byte per pillar]
+    Q.touched = (P.bev_layout == FIERY_BEV_NHWC)
+                    ? nullptr
+                    : reinterpret_cast<unsigned char*>(scratch + static_cast<size_t>(P.n_frames) * P.pillars * P.C);
+    rc = launch_forward_t<6>(map, Q, stream);
+    if (rc != FIERY_OK) return rc;
+    if (P.bev_layout == FIERY_BEV_NCHW) {
+        const int bpf = static_cast<int>((P.pillars + FIN_THREADS - 1) / FIN_THREADS);
+        finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * P.n_frames, 256, 0, stream>>>(scratch, Q.touched, bev_out, P.pillars, bpf);
+        FIERY_CUDA_CHECK(cudaGetLastError());
     }
-    return launch_forward_t<6>(map, Q, stream);
+    return FIERY_OK;
 }
 
 int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t stream) {

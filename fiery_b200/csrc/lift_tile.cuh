@@ -32,9 +32,6 @@ struct LiftParams {
     const float* fd;         // (D) frustum depth                     fiery.py:115
     float* accum;            // forward: (B', X*Y, C) channel-last accumulation target
     unsigned char* touched;  // forward, NCHW output: (B', X*Y) byte map of pillars that received a point
-    float* bev;              // forward, NCHW output: (B', C, X*Y)
-    int* queue;              // forward: work queue counters (zero between launches)
-    int n_items, tiles_per_frame, fin_chunks_per_frame, fin_lag;
     const float* grad_bev;   // backward: (B', X*Y, C) or (B', C, X*Y)
     float* grad_head;        // backward output
     int bev_layout;

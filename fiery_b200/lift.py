@@ -283,16 +283,17 @@ class LiftSplat(nn.Module):
             if self.output_layout == "channels_last":
                 desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NHWC)
                 store = torch.zeros((B, X, Y, C), dtype=torch.float32, device=dev)
-                out = store.permute(0, 3, 1, 2)
+                out, scratch_ptr = store.permute(0, 3, 1, 2), 0
             else:
                 desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NCHW)
                 store = torch.empty((B, C, X, Y), dtype=torch.float32, device=dev)
                 out = store
-            if scratch is None and B:
-                scratch = _scratch.get(dev, int(lib.fiery_lift_scratch_bytes(desc)))
+                if scratch is None and B:
+                    scratch = _scratch.get(dev, int(lib.fiery_lift_scratch_bytes(desc)))
+                scratch_ptr = scratch.data_ptr() if B else 0
             _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
-                                              c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(),
-                                              scratch.data_ptr() if B else 0, _stream_ptr(dev)), "fiery_lift_forward")
+                                              c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
+                                              _stream_ptr(dev)), "fiery_lift_forward")
         return out
 
     def _launch_backward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
@@ -338,9 +339,8 @@ class GraphedLift:
         c = module._constants(dev)
         B, n = intrinsics.shape[:2]
         self.scratch = None
-        if B:
-            layout = _lib.BEV_NHWC if module.output_layout == "channels_last" else _lib.BEV_NCHW
-            desc = module._desc(c, B, n, head.dtype, _lib.CALIB_RAW, layout)
+        if module.output_layout != "channels_last" and B:
+            desc = module._desc(c, B, n, head.dtype, _lib.CALIB_RAW, _lib.BEV_NCHW)
             self.scratch = torch.zeros(int(_lib.load().fiery_lift_scratch_bytes(desc)) // 4, dtype=torch.float32, device=dev)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()

@@ -84,18 +84,16 @@ typedef struct fiery_lift_desc {
 FIERY_API int fiery_abi_version(void);
 FIERY_API const char* fiery_last_error(void);
 
-/* Bytes of zero-initialised, 256-byte aligned device scratch fiery_lift_forward needs: the work-queue counters of the
- * persistent kernel and, for FIERY_BEV_NCHW output, a channel-last fp32 accumulator (B', X*Y, C) plus one "touched"
- * byte per pillar.  Invariant: the scratch must be all zero on entry; it is all zero again when the call's work
- * completes, so one buffer per stream can be allocated and cleared once and reused by every call. */
+/* Bytes of zero-initialised device scratch fiery_lift_forward needs for FIERY_BEV_NCHW output (0 for NHWC): a
+ * channel-last fp32 accumulator (B', X*Y, C) followed by one "touched" byte per pillar.
+ * Invariant: the scratch must be all zero on entry; it is all zero again when the call's work completes. */
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* desc);
 
 /*
  * Forward lift.  head: (B'*n, D+C, h, w) [C channels if !use_depth_distribution], dtype head_dtype.
  * frustum_u (w), frustum_v (h), frustum_d (D): the separable factors of Fiery.frustum (fiery.py:109-128), fp32.
  * bev_out: (B',C,X,Y) fp32 in bev_layout.  For FIERY_BEV_NHWC the caller must pass bev_out zero-filled (the kernel
- * accumulates into it).  One launch: a persistent kernel pulls tile items (lift) and, for NCHW, finalize items (layout
- * pass) from a queue.
+ * accumulates into it) and scratch may be NULL.
  */
 FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                        const float* frustum_u, const float* frustum_v, const float* frustum_d,

@@ -44,7 +44,7 @@ def test_argument_validation_without_gpu():
         d.bev_resolution[a] = 1.0
     rc = lib.fiery_lift_forward(d, 16, 16, 16, 16, 16, 16, 16, 16, None)
     assert rc == -1 and b"bev_z" in lib.fiery_last_error()
-    assert lib.fiery_lift_scratch_bytes(d) == 256 + 1 * 50 * 50 * 64 * 4 + 2512   # queue + accumulator + touched map
+    assert lib.fiery_lift_scratch_bytes(d) == 1 * 50 * 50 * 64 * 4 + 2512      # accumulator + touched-pillar byte map
     n = ctypes.c_int64(-1)
     assert lib.fiery_voxels_summing_plan(0, None, None, ctypes.byref(n), None) == 0 and n.value == 0
 
