@@ -78,6 +78,7 @@ int encode_head_maps(HeadMaps* maps, const void* head, int dtype, const LiftPara
 
 // launchers defined next to their kernels
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch, cudaStream_t);
+int lift_chunk_frames(int n_frames, long long pillars, int channels);
 int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, float* workspace, cudaStream_t);
 int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t);
 int launch_compose(int n, const float* K, const float* E, float* combined, float* translation, cudaStream_t);
@@ -101,7 +102,7 @@ static int make_params(const fiery_lift_desc_t* d, const float* calib_a, const f
     FIERY_REQUIRE(d->n_frames == 0 || (calib_a && calib_b), "calibration pointer is NULL");
     FIERY_REQUIRE(fu && fv && fd, "frustum pointer is NULL");
     for (int a = 0; a < 3; ++a) FIERY_REQUIRE(d->bev_resolution[a] > 0.f, "bev_resolution[%d] must be positive", a);
-    P.n_frames = d->n_frames; P.n_cameras = d->n_cameras;
+    P.n_frames = d->n_frames; P.n_cameras = d->n_cameras; P.frame0 = 0;
     P.D = d->depth_bins; P.C = d->channels; P.hh = d->feat_h; P.ww = d->feat_w;
     P.n_wtiles = (d->feat_w + WT - 1) / WT;
     P.use_depth = d->use_depth_distribution ? 1 : 0;
@@ -126,8 +127,9 @@ FIERY_API int fiery_abi_version(void) { return FIERY_B200_ABI_VERSION; }
 FIERY_API const char* fiery_last_error(void) { return g_last_error; }
 
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
-    if (!d || d->bev_layout != FIERY_BEV_NCHW) return 0;
-    const size_t pillars = static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y;
+    if (!d || d->bev_layout != FIERY_BEV_NCHW || d->n_frames <= 0) return 0;
+    const long long per_frame = static_cast<long long>(d->bev_x) * d->bev_y;
+    const size_t pillars = static_cast<size_t>(lift_chunk_frames(d->n_frames, per_frame, d->channels)) * per_frame;   // one chunk of frames
     return pillars * d->channels * sizeof(float) + ((pillars + 15) & ~static_cast<size_t>(15));   // accumulator + touched map
 }
 

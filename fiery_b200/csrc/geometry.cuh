@@ -172,4 +172,20 @@ __device__ __forceinline__ int pillar_of(const GridParams& g, const float p[3]) 
     return ok ? ix * g.Y + iy : -1;
 }
 
+// Same mask-and-rank as pillar_of, as one predicate chain (6 setp + selp): ordered comparisons are false for NaN.
+__device__ __forceinline__ int select_pillar(float sx, float sy, float az, float Xf, float Yf, float z_lo, float z_hi, int rank) {
+    int r;
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.gt.f32 p, %1, 0fBF800000;\n\t"
+        "setp.lt.and.f32 p, %1, %4, p;\n\t"
+        "setp.gt.and.f32 p, %2, 0fBF800000, p;\n\t"
+        "setp.lt.and.f32 p, %2, %5, p;\n\t"
+        "setp.ge.and.f32 p, %3, %6, p;\n\t"
+        "setp.le.and.f32 p, %3, %7, p;\n\t"
+        "selp.s32 %0, %8, -1, p;\n\t}"
+        : "=r"(r)
+        : "f"(sx), "f"(sy), "f"(az), "f"(Xf), "f"(Yf), "f"(z_lo), "f"(z_hi), "r"(rank));
+    return r;
+}
+
 }  // namespace fiery

@@ -45,10 +45,11 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
     extern __shared__ __align__(128) unsigned char smem[];
     const TL L(P.hh, P.C);
 
-    // tile coordinates: blockIdx.x = (frame*n + camera) * n_wtiles + wtile
+    // tile coordinates: blockIdx.x = (chunk-local frame * n + camera) * n_wtiles + wtile
     const int wtile = blockIdx.x % P.n_wtiles;
-    const int img = blockIdx.x / P.n_wtiles;          // flat (frame, camera)
-    const int frame = img / P.n_cameras;
+    const int img_local = blockIdx.x / P.n_wtiles;    // (frame, camera) within this launch's chunk of frames
+    const int img = P.frame0 * P.n_cameras + img_local;
+    const int frame = img_local / P.n_cameras;        // chunk-local: indexes the accumulator
     const int w0 = wtile * WT;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -242,6 +243,15 @@ static int launch_forward_t(const HeadMaps& map, const LiftParams& P, cudaStream
     return FIERY_OK;
 }
 
+// Frames per launch for NCHW output: as many as keep the channel-last accumulator within ~40 MB (L2-resident).
+int lift_chunk_frames(int n_frames, long long pillars, int channels) {
+    const long long per_frame = pillars * channels * 4 + pillars;
+    long long c = (40ll << 20) / (per_frame > 0 ? per_frame : 1);
+    if (c < 1) c = 1;
+    if (c > n_frames) c = n_frames;
+    return static_cast<int>(c < 1 ? 1 : c);
+}
+
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch,
                         cudaStream_t stream) {
     FIERY_REQUIRE(head_dtype == FIERY_DTYPE_F32, "head dtype %d not supported by this build (fp32 only)", head_dtype);
@@ -252,16 +262,25 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     int rc = encode_head_maps(&map, head, head_dtype, P);
     if (rc != FIERY_OK) return rc;
     LiftParams Q = P;
-    Q.accum = (P.bev_layout == FIERY_BEV_NHWC) ? bev_out : scratch;
-    // scratch = [accumulator floats][one "touched" byte per pillar]
-    Q.touched = (P.bev_layout == FIERY_BEV_NHWC)
-                    ? nullptr
-                    : reinterpret_cast<unsigned char*>(scratch + static_cast<size_t>(P.n_frames) * P.pillars * P.C);
-    rc = launch_forward_t<6>(map, Q, stream);
-    if (rc != FIERY_OK) return rc;
-    if (P.bev_layout == FIERY_BEV_NCHW) {
-        const int bpf = static_cast<int>((P.pillars + FIN_THREADS - 1) / FIN_THREADS);
-        finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * P.n_frames, 256, 0, stream>>>(scratch, Q.touched, bev_out, P.pillars, bpf);
+    if (P.bev_layout == FIERY_BEV_NHWC) {          // the caller's zero-filled channel-last tensor is the accumulator
+        Q.accum = bev_out;
+        Q.touched = nullptr;
+        Q.frame0 = 0;
+        return launch_forward_t<6>(map, Q, stream);
+    }
+    // NCHW: frames are processed in chunks whose accumulator (chunk x 10 MB at 200x200) stays resident in the 126 MB L2
+    // between the reductions of lift_forward_kernel and the layout pass, so the scratch never costs HBM traffic
+    const int chunk = lift_chunk_frames(P.n_frames, P.pillars, P.C);
+    Q.accum = scratch;                             // [accumulator floats of one chunk][one "touched" byte per pillar]
+    Q.touched = reinterpret_cast<unsigned char*>(scratch + static_cast<size_t>(chunk) * P.pillars * P.C);
+    const int bpf = static_cast<int>((P.pillars + FIN_THREADS - 1) / FIN_THREADS);
+    for (int f0 = 0; f0 < P.n_frames; f0 += chunk) {
+        Q.frame0 = f0;
+        Q.n_frames = (P.n_frames - f0 < chunk) ? P.n_frames - f0 : chunk;
+        rc = launch_forward_t<6>(map, Q, stream);
+        if (rc != FIERY_OK) return rc;
+        finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * Q.n_frames, FIN_THREADS, 0, stream>>>(
+            Q.accum, Q.touched, bev_out + static_cast<size_t>(f0) * P.C * P.pillars, P.pillars, bpf);
         FIERY_CUDA_CHECK(cudaGetLastError());
     }
     return FIERY_OK;

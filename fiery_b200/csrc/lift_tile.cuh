@@ -20,6 +20,7 @@ constexpr int CG = 16;       // channel groups of 4 -> C = 64
 
 struct LiftParams {
     int n_frames, n_cameras;
+    int frame0;              // first frame of this launch (frames are processed in chunks)
     int D, C, hh, ww;
     int n_wtiles;            // ceil(ww / WT)
     int head_channels;       // D + C, or C without the depth distribution
@@ -98,8 +99,8 @@ __device__ __forceinline__ void stage_camera(const LiftParams& P, const TileLayo
 }
 
 // ---- pillar (rank, fiery.py:236-256) of every point of the tile: WT x D x h evaluations of the reference arithmetic -------
-template <int DBLKS>
-__device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem, int w0) {
+template <int DBLKS, bool POW2>
+__device__ __forceinline__ void stage_pillars_impl(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem, int w0) {
     constexpr int DPAD = TileLayout<DBLKS>::DPAD;
     constexpr int NHS = 2;                                  // row halves, so that WT*DPAD*NHS == NT work items
     const float* s_cam = reinterpret_cast<const float*>(smem + L.off_cam);
@@ -112,7 +113,12 @@ __device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLay
     for (int i = 0; i < 9; ++i) T.m[i] = s_cam[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) T.t[i] = s_cam[9 + i];
-    const GridParams g = P.grid;                            // registers, not constant-bank reloads in the loop
+    // grid constants as plain floats (hoisted out of the point loop)
+    const float offx = P.grid.off[0], offy = P.grid.off[1], offz = P.grid.off[2];
+    const float kx = POW2 ? P.grid.inv_res[0] : P.grid.res[0], ky = POW2 ? P.grid.inv_res[1] : P.grid.res[1];
+    const float Xf = static_cast<float>(P.grid.X), Yf = static_cast<float>(P.grid.Y);
+    const float z_lo = P.grid.z_lo, z_hi = P.grid.z_hi;
+    const int Y = P.grid.Y;
     for (int item = threadIdx.x; item < WT * DPAD * NHS; item += blockDim.x) {
         const int d = item % DPAD;
         const int wt = (item / DPAD) % WT;
@@ -128,10 +134,20 @@ __device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLay
 #pragma unroll 2
         for (int h = h_lo; h < h_hi; ++h, out += DPAD) {
             float p[3];
-            ego_point(T, ct, s_v[h], depth, p);
-            *out = pillar_of(g, p);
+            ego_point(T, ct, s_v[h], depth, p);                               // fiery.py:199-205
+            const float ax = __fsub_rn(p[0], offx), ay = __fsub_rn(p[1], offy), az = __fsub_rn(p[2], offz);
+            const float sx = POW2 ? __fmul_rn(ax, kx) : __fdiv_rn(ax, kx);    // fiery.py:236 (x scale exact when res is 2^k)
+            const float sy = POW2 ? __fmul_rn(ay, ky) : __fdiv_rn(ay, ky);
+            const int rank = static_cast<int>(sx) * Y + static_cast<int>(sy); // truncation, fiery.py:237,252-256
+            *out = select_pillar(sx, sy, az, Xf, Yf, z_lo, z_hi, rank);       // mask, fiery.py:240-247
         }
     }
+}
+
+template <int DBLKS>
+__device__ __forceinline__ void stage_pillars(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem, int w0) {
+    if (P.grid.pow2[0] && P.grid.pow2[1]) stage_pillars_impl<DBLKS, true>(P, L, smem, w0);
+    else stage_pillars_impl<DBLKS, false>(P, L, smem, w0);
 }
 
 // chg[pix][dblk]: bit j set <=> pillar[pix][8*dblk+j] differs from the previous row's (same column).  Row 0 -> 0.
