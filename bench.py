@@ -244,6 +244,20 @@ def main():
     t_eager = timed_steps(step_eager, S)
     barrier()
 
+    # ---- forward + backward through autograd (the training-step view of the same path) -----------------------------------
+    gout_d = torch.from_numpy(make_grad_bev(cfg, seed=100 + rank)).to(dev)
+    head_g = head_d.clone().requires_grad_(True)
+
+    def step_fwd_bwd():
+        head_g.grad = None
+        lift(head_g, K_d, E_d).backward(gout_d)
+
+    for _ in range(3):
+        step_fwd_bwd()
+    barrier()
+    t_fb = timed_steps(step_fwd_bwd, S)
+    barrier()
+
     # ---- e2e: pinned host inputs, host copy of the result, all inside the timed region ---------------------------------
     head_h = torch.from_numpy(head_np).pin_memory()
     K_h, E_h = torch.from_numpy(K).pin_memory(), torch.from_numpy(E).pin_memory()
@@ -296,6 +310,7 @@ def main():
 
     ms_dev = reduce_max(float(np.mean(t_dev)))
     ms_eager = reduce_max(float(np.mean(t_eager)))
+    ms_fb = reduce_max(float(np.mean(t_fb)))
     ms_e2e = reduce_max(float(np.mean(t_e2e)))
     ms_kernel = reduce_max(float(np.mean(t_kernel)))
     ms_both = reduce_max(float(np.mean(t_both)))
@@ -310,6 +325,8 @@ def main():
             "warmup": W, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "value_eager": total_frames / (ms_eager * 1e-3), "ms_per_step_eager": ms_eager,
+            "fwd_bwd": {"value": total_frames / (ms_fb * 1e-3), "unit": "frames/s", "ms_per_step": ms_fb,
+                        "what": "LiftSplat.forward + autograd backward to the head tensor (eager)"},
             "config": {"workload": cfg.name, "frames_per_step_per_gpu": frames, "n_cameras": cfg.n_cameras,
                        "final_dim": list(cfg.final_dim), "feat_hw": list(cfg.feat_hw), "depth_bins": cfg.depth_bins,
                        "channels": cfg.out_channels, "bev": [X, Y], "direction": "forward", "output_layout": args.layout,

@@ -243,10 +243,12 @@ static int launch_forward_t(const HeadMaps& map, const LiftParams& P, cudaStream
     return FIERY_OK;
 }
 
-// Frames per launch for NCHW output: as many as keep the channel-last accumulator within ~40 MB (L2-resident).
+// Frames per launch for NCHW output.  Measured on B200 (profiles/r01_notes.md): chunks small enough to keep the accumulator
+// L2-resident (3 frames, 31 MB) are slower end to end (152.9 us vs 122.7 us for 9 frames) -- the extra launches and the
+// single-wave grids cost more than the saved HBM traffic -- so the chunk only bounds the scratch footprint (1 GiB).
 int lift_chunk_frames(int n_frames, long long pillars, int channels) {
     const long long per_frame = pillars * channels * 4 + pillars;
-    long long c = (40ll << 20) / (per_frame > 0 ? per_frame : 1);
+    long long c = (1ll << 30) / (per_frame > 0 ? per_frame : 1);
     if (c < 1) c = 1;
     if (c > n_frames) c = n_frames;
     return static_cast<int>(c < 1 ? 1 : c);
@@ -268,8 +270,7 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
         Q.frame0 = 0;
         return launch_forward_t<6>(map, Q, stream);
     }
-    // NCHW: frames are processed in chunks whose accumulator (chunk x 10 MB at 200x200) stays resident in the 126 MB L2
-    // between the reductions of lift_forward_kernel and the layout pass, so the scratch never costs HBM traffic
+    // NCHW: lift into the channel-last accumulator, then the layout pass; chunked only to bound the scratch footprint
     const int chunk = lift_chunk_frames(P.n_frames, P.pillars, P.C);
     Q.accum = scratch;                             // [accumulator floats of one chunk][one "touched" byte per pillar]
     Q.touched = reinterpret_cast<unsigned char*>(scratch + static_cast<size_t>(chunk) * P.pillars * P.C);

@@ -358,16 +358,21 @@ class _LiftSplatFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, head, intrinsics, extrinsics, module: LiftSplat):
-        out = module._launch_forward(head, intrinsics, extrinsics)
+        # Under AMP (baseline.yml PRECISION 16) depth_layer emits fp16; the reference's softmax autocasts to fp32 and the
+        # fp32 x fp16 outer product promotes to fp32 (encoder.py:99-100), so the lift itself is fp32 there too.  This build's
+        # kernels read an fp32 head tensor: half-precision logits are widened on the device first.
+        ctx.head_dtype = head.dtype
+        head32 = head if head.dtype == torch.float32 else head.float()
+        out = module._launch_forward(head32, intrinsics, extrinsics)
         ctx.module = module
-        ctx.save_for_backward(head, intrinsics, extrinsics)
+        ctx.save_for_backward(head32, intrinsics, extrinsics)
         return out
 
     @staticmethod
     def backward(ctx, grad_bev):
         head, intrinsics, extrinsics = ctx.saved_tensors
         grad_head = ctx.module._launch_backward(head, intrinsics, extrinsics, grad_bev)
-        return grad_head, None, None, None     # calibration is data: no gradient (geometry.py:300)
+        return grad_head.to(ctx.head_dtype), None, None, None     # calibration is data: no gradient (geometry.py:300)
 
 
 def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):

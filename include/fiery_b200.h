@@ -86,7 +86,7 @@ FIERY_API const char* fiery_last_error(void);
 
 /* Bytes of zero-initialised device scratch fiery_lift_forward needs for FIERY_BEV_NCHW output (0 for NHWC): a
  * channel-last fp32 accumulator (chunk, X*Y, C) followed by one "touched" byte per pillar, where chunk <= B' is the number
- * of frames processed per launch (sized so that the accumulator stays L2-resident, ~40 MB).
+ * of frames processed per launch (all of them unless the accumulator would exceed 1 GiB).
  * Invariant: the scratch must be all zero on entry; it is all zero again when the call's work completes. */
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* desc);
 

@@ -1,0 +1,55 @@
+"""CPU: install()/uninstall() rebind the reference's call sites -- exercised on a stand-in `fiery`
+package with the same module paths and symbol names as the reference (fiery/models/fiery.py:10,275,
+fiery/utils/geometry.py:283); the real reference cannot be imported on the test box."""
+import importlib
+import sys
+import textwrap
+
+import pytest
+
+
+@pytest.fixture
+def fake_fiery(tmp_path, monkeypatch):
+    root = tmp_path / "fiery"
+    (root / "models").mkdir(parents=True)
+    (root / "utils").mkdir()
+    for d in (root, root / "models", root / "utils"):
+        (d / "__init__.py").write_text("")
+    (root / "utils" / "geometry.py").write_text(textwrap.dedent("""
+        class VoxelsSumming:            # stands for fiery/utils/geometry.py:283
+            tag = "reference"
+    """))
+    (root / "models" / "fiery.py").write_text(textwrap.dedent("""
+        from fiery.utils.geometry import VoxelsSumming          # bound at import, like fiery/models/fiery.py:10
+
+        class Fiery:
+            def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):   # fiery.py:275
+                return "reference"
+    """))
+    monkeypatch.syspath_prepend(str(tmp_path))
+    for name in [m for m in sys.modules if m == "fiery" or m.startswith("fiery.")]:
+        monkeypatch.delitem(sys.modules, name)
+    yield
+    for name in [m for m in sys.modules if m == "fiery" or m.startswith("fiery.")]:
+        sys.modules.pop(name, None)
+
+
+def test_install_rebinds_and_uninstall_restores(fake_fiery):
+    import fiery_b200.install as fb
+    from fiery_b200.geometry import VoxelsSumming as ours
+    from fiery_b200.lift import calculate_birds_eye_view_features as ours_bev
+
+    geometry = importlib.import_module("fiery.utils.geometry")
+    fiery_mod = importlib.import_module("fiery.models.fiery")
+    ref_vs, ref_bev = geometry.VoxelsSumming, fiery_mod.Fiery.calculate_birds_eye_view_features
+
+    fb.install(level="voxels_summing")
+    assert geometry.VoxelsSumming is ours and fiery_mod.VoxelsSumming is ours      # both bindings (fiery.py:10)
+    assert fiery_mod.Fiery.calculate_birds_eye_view_features is ref_bev
+    fb.install()                                                                    # level="fused"
+    assert fiery_mod.Fiery.calculate_birds_eye_view_features is ours_bev
+    fb.uninstall()
+    assert geometry.VoxelsSumming is ref_vs and fiery_mod.VoxelsSumming is ref_vs
+    assert fiery_mod.Fiery.calculate_birds_eye_view_features is ref_bev
+    with pytest.raises(ValueError):
+        fb.install(level="nope")

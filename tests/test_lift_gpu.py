@@ -224,3 +224,54 @@ def test_graph_capture_and_host_pipeline_match_eager():
     out1 = lift.lift_from_host(head.pin_memory(), torch.from_numpy(K).pin_memory(), torch.from_numpy(E).pin_memory(),
                                device=dev, chunk_frames=5)
     assert O.normwise_error(out1, out) < 1e-6
+
+
+def test_reference_call_site_signature_and_amp_head():
+    """fiery_b200.lift.calculate_birds_eye_view_features has the signature and return shape of
+    Fiery.calculate_birds_eye_view_features (fiery/models/fiery.py:275-286): x (b,s,n,3,H,W) -> (b,s,C,X,Y).  The stand-in
+    model carries the attributes the reference module has (encoder.get_features / depth_layer / use_depth_distribution,
+    frustum, bev_*), with a tiny conv as backbone; fp16 head tensors (AMP, baseline.yml PRECISION 16) are accepted."""
+    import types
+    from fiery_b200.lift import calculate_birds_eye_view_features
+    cfg = LiftConfig(**{**CONFIGS["cfg1_tiny"].__dict__, "frames": 2})
+    dev = _dev()
+    torch.manual_seed(0)
+    H, W = cfg.final_dim
+
+    class Enc(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.use_depth_distribution = True
+            self.feat = torch.nn.Conv2d(3, 16, 8, stride=8)
+            self.depth_layer = torch.nn.Conv2d(16, cfg.head_channels, 1)
+
+        def get_features(self, x):
+            return self.feat(x)
+
+    proto = LiftSplat.from_config(cfg)
+    model = types.SimpleNamespace(encoder=Enc().to(dev), frustum=proto.frustum, bev_resolution=proto.bev_resolution,
+                                  bev_start_position=proto.bev_start_position, bev_dimension=proto.bev_dimension,
+                                  encoder_out_channels=cfg.out_channels)
+    b, s, n = 1, 2, cfg.n_cameras
+    x = torch.randn(b, s, n, 3, H, W, device=dev)
+    K, E = make_calibration(cfg, seed=8)
+    K = torch.from_numpy(K).view(b, s, n, 3, 3).to(dev)
+    E = torch.from_numpy(E).view(b, s, n, 4, 4).to(dev)
+    out = calculate_birds_eye_view_features(model, x, K, E)
+    assert tuple(out.shape) == (b, s, cfg.out_channels, *cfg.bev_hw)
+    with torch.no_grad():
+        head = model.encoder.depth_layer(model.encoder.get_features(x.view(b * s * n, 3, H, W)))
+    exact = O.LiftOracle.from_config(cfg).lift_exact(head.cpu(), K.view(b * s, n, 3, 3).cpu(), E.view(b * s, n, 4, 4).cpu())
+    assert O.normwise_error(out.detach().view(b * s, *out.shape[2:]).cpu(), exact) < TOL
+    out.sum().backward()                                   # gradients reach the encoder's parameters through the lift
+    assert model.encoder.depth_layer.weight.grad is not None and model.encoder.feat.weight.grad.abs().sum() > 0
+    # AMP: fp16 head in, fp32 BEV out, fp16 gradient back
+    lift = LiftSplat.from_config(cfg).to(dev)
+    h16 = head.half().requires_grad_(True)
+    bev16 = lift(h16, K.view(b * s, n, 3, 3), E.view(b * s, n, 4, 4))
+    assert bev16.dtype == torch.float32
+    exact16 = O.LiftOracle.from_config(cfg).lift_exact(h16.detach().float().cpu(), K.view(b * s, n, 3, 3).cpu(),
+                                                       E.view(b * s, n, 4, 4).cpu())
+    assert O.normwise_error(bev16.detach().cpu(), exact16) < TOL
+    bev16.sum().backward()
+    assert h16.grad.dtype == torch.float16
