@@ -17,12 +17,41 @@
 
 namespace fiery {
 
-constexpr int MAXR = 6;   // rows per thread; host checks ceil(h / (threads/64)) <= MAXR
+constexpr int MAXR = 5;   // rows per thread; host checks ceil(h / (threads/64)) <= MAXR (h <= 30)
 
-__device__ __forceinline__ float4 ldg_f4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// packed fp32x2 helpers (SASS FFMA2 / FMUL2)
+__device__ __forceinline__ void fma2_bcast(unsigned long long& acc, float a, unsigned long long b) {
+    unsigned long long aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(aa), "l"(b));
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float pair_sum(unsigned long long v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo + hi;
+}
+// In-place predicated updates of a register pair (straight-line for the compiler: a conditional C++ assignment inside the
+// row loop makes ptxas shuffle the whole register set every iteration, see profiles/r01_notes.md).
+__device__ __forceinline__ void clear_pair_if(unsigned long long& a, unsigned long long& b, unsigned pred) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p mov.b64 %0, 0;\n\t@p mov.b64 %1, 0;\n\t}" : "+l"(a), "+l"(b) : "r"(pred));
+}
+__device__ __forceinline__ void load_pair_if(unsigned long long& a, unsigned long long& b, const float* ptr, bool pred) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.v2.b64 {%0, %1}, [%2];\n\t}"
+                 : "+l"(a), "+l"(b) : "l"(ptr), "r"(static_cast<unsigned>(pred)) : "memory");
+}
 
 template <int DBLKS>
-__global__ void __launch_bounds__(64 * DBLKS, 1)
+__global__ void __launch_bounds__(64 * DBLKS, 2)
 lift_backward_kernel(const __grid_constant__ HeadMaps head_maps, const __grid_constant__ HeadMaps grad_maps,
                      const LiftParams P) {
     using TL = TileLayout<DBLKS>;
@@ -71,22 +100,23 @@ lift_backward_kernel(const __grid_constant__ HeadMaps head_maps, const __grid_co
     const int h_lo = (hh * hq) / HQ, h_hi = (hh * (hq + 1)) / HQ;
     const float* gbev = P.grad_bev + static_cast<size_t>(frame) * P.pillars * P.C + cg * 4;   // channel-last
 
-    float gc[MAXR][4];
+    // accumulators and gradient vectors as fp32x2 pairs: (c0,c1) and (c2,c3) of this lane's 4 channels
+    unsigned long long gc[MAXR][2];
 #pragma unroll
-    for (int r = 0; r < MAXR; ++r) gc[r][0] = gc[r][1] = gc[r][2] = gc[r][3] = 0.f;
+    for (int r = 0; r < MAXR; ++r) gc[r][0] = gc[r][1] = 0ull;
 
     const bool b3 = cg & 8, b2 = cg & 4, b1 = cg & 2;
     const int jsel = (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);   // the depth (within the block) this lane ends up owning
 
     for (int dblk = 0; dblk < DBLKS; ++dblk) {
-        float G[8][4];
+        unsigned long long G[8][2];
         {
             const int* pl = s_pillar + (wt * hh + h_lo) * DPAD + dblk * 8;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int p = (h_lo < h_hi) ? pl[j] : -1;
-                const float4 g = (p >= 0) ? ldg_f4(gbev + static_cast<size_t>(p) * P.C) : make_float4(0.f, 0.f, 0.f, 0.f);
-                G[j][0] = g.x; G[j][1] = g.y; G[j][2] = g.z; G[j][3] = g.w;
+                G[j][0] = G[j][1] = 0ull;
+                load_pair_if(G[j][0], G[j][1], gbev + static_cast<size_t>(static_cast<unsigned>(p < 0 ? 0 : p)) * P.C, p >= 0);
             }
         }
 #pragma unroll
@@ -96,30 +126,28 @@ lift_backward_kernel(const __grid_constant__ HeadMaps head_maps, const __grid_co
                 const int pix = wt * hh + h;
                 if (r > 0) {
                     const unsigned m = s_chg[pix * DBLKS + dblk];
-                    if (m) {
+                    if (m) {     // some depth of this block enters another pillar at this row: fetch its gradient vector
+                        const int* pl_row = s_pillar + pix * DPAD + dblk * 8;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            if (m & (1u << j)) {
-                                const int p = s_pillar[pix * DPAD + dblk * 8 + j];
-                                const float4 g = (p >= 0) ? ldg_f4(gbev + static_cast<size_t>(p) * P.C)
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-                                G[j][0] = g.x; G[j][1] = g.y; G[j][2] = g.z; G[j][3] = g.w;
-                            }
+                            const unsigned bit = m & (1u << j);
+                            const int p = bit ? pl_row[j] : -1;
+                            clear_pair_if(G[j][0], G[j][1], bit);
+                            load_pair_if(G[j][0], G[j][1], gbev + static_cast<size_t>(static_cast<unsigned>(p < 0 ? 0 : p)) * P.C, p >= 0);
                         }
                     }
                 }
                 const float4 p0 = *reinterpret_cast<const float4*>(s_prob + pix * PS + dblk * 8);
                 const float4 p1 = *reinterpret_cast<const float4*>(s_prob + pix * PS + dblk * 8 + 4);
-                const float4 c = *reinterpret_cast<const float4*>(s_ctx + pix * L.C + cg * 4);
+                const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(s_ctx + pix * L.C + cg * 4);
                 const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
                 float gp[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    gc[r][0] = fmaf(pv[j], G[j][0], gc[r][0]);
-                    gc[r][1] = fmaf(pv[j], G[j][1], gc[r][1]);
-                    gc[r][2] = fmaf(pv[j], G[j][2], gc[r][2]);
-                    gc[r][3] = fmaf(pv[j], G[j][3], gc[r][3]);
-                    gp[j] = fmaf(c.w, G[j][3], fmaf(c.z, G[j][2], fmaf(c.y, G[j][1], c.x * G[j][0])));
+                    fma2_bcast(gc[r][0], pv[j], G[j][0]);                       // g_ctx += prob * G
+                    fma2_bcast(gc[r][1], pv[j], G[j][1]);
+                    const unsigned long long t = fma2(c.y, G[j][1], mul2(c.x, G[j][0]));   // ctx . G over this lane's 4 channels
+                    gp[j] = pair_sum(t);
                 }
                 if (P.use_depth) {
                     // transposing butterfly over the 16 channel lanes: 8 values -> 1 per lane, summed over all 16 lanes
@@ -153,7 +181,7 @@ lift_backward_kernel(const __grid_constant__ HeadMaps head_maps, const __grid_co
     for (int r = 0; r < MAXR; ++r) {
         const int h = h_lo + r;
         if (h < h_hi)
-            *reinterpret_cast<float4*>(s_ctx + (wt * hh + h) * L.C + cg * 4) = make_float4(gc[r][0], gc[r][1], gc[r][2], gc[r][3]);
+            *reinterpret_cast<ulonglong2*>(s_ctx + (wt * hh + h) * L.C + cg * 4) = make_ulonglong2(gc[r][0], gc[r][1]);
     }
     __syncthreads();
 

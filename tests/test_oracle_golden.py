@@ -111,3 +111,27 @@ def test_exact_pooling_is_the_adjudicator(golden_lift):
     assert O.normwise_error(exact, torch.from_numpy(golden_lift[f"{tag}__bev_exact"])) < 1e-12
     ref = torch.from_numpy(golden_lift[f"{tag}__bev_ref"])
     assert O.normwise_error(ref, exact) < 1e-4
+
+
+@pytest.mark.parametrize("case", FAST_CASES, ids=case_id)
+def test_c_restatement_agrees(golden_lift, case):
+    """oracle/lift_oracle.c (gcc -ffp-contract=off) reproduces the reference's voxel indices bit for bit and its exact
+    pooling agrees with the torch fp64 pooling."""
+    from oracle import c_oracle
+    cfg, K, E, head, _ = build_case(case)
+    tag = golden_tag(case)
+    oracle = O.LiftOracle.from_config(cfg)
+    comb = golden_lift[f"{tag}__combined"]
+    trans = golden_lift[f"{tag}__translation"]
+    fr = oracle.frustum
+    off = (oracle.start - oracle.resolution / 2.0).numpy()
+    idx, keep = c_oracle.voxel_indices(fr[0, 0, :, 0].numpy(), fr[0, :, 0, 1].numpy(), fr[:, 0, 0, 2].numpy(), comb, trans, off,
+                                       oracle.resolution.numpy(), oracle.dimension.numpy())
+    assert sha(idx) == golden_str(golden_lift[f"{tag}__idx_sha256"])
+    assert sha(keep) == golden_str(golden_lift[f"{tag}__keep_sha256"])
+    D, C = cfg.depth_bins, cfg.out_channels
+    prob = head[:, :D].double().softmax(1).numpy()
+    X, Y = cfg.bev_hw
+    bev = c_oracle.pool_exact(prob, head[:, D:].double().numpy(), idx, keep, cfg.n_cameras, X, Y)
+    exact = oracle.lift_exact(head, K, E, combined=torch.from_numpy(comb))
+    assert O.normwise_error(torch.from_numpy(bev), exact) < 1e-13
