@@ -49,7 +49,7 @@ struct TileLayout {
 
     int hh, C, PX;                               // PX = hh * WT pixels per tile
     // byte offsets into dynamic shared memory
-    int off_bar, off_cam, off_brk, off_u, off_v, off_d, off_prob, off_ctx, off_pillar, off_chg, total;
+    int off_bar, off_cam, off_brk, off_u, off_v, off_d, off_red, off_prob, off_ctx, off_pillar, off_chg, total;
 
     __host__ __device__ TileLayout(int hh_, int C_) : hh(hh_), C(C_), PX(hh_ * WT) {
         int o = 0;
@@ -59,6 +59,7 @@ struct TileLayout {
         off_u = o;      o += WT * 4;
         off_d = o;      o += DPAD * 4;
         off_v = o;      o += ((hh + 3) & ~3) * 4;
+        off_red = o;    o += 2 * (DPAD / 16) * PX * 4;   // softmax partial max / sum per (depth group of 16, pixel)
         o = (o + 127) & ~127;
         const int prob_raw = DPAD * PX * 4, prob_t = PX * PS * 4;
         off_prob = o;   o += (prob_raw > prob_t ? prob_raw : prob_t);
@@ -197,81 +198,108 @@ __device__ __forceinline__ void issue_tile_loads(const LiftParams& P, const Tile
 }
 
 // ---- phase 2: softmax over depth + in-place transposes ---------------------------------------------------------------
-// Warp-specialised, one "unit" per warp, all units run concurrently (host checks units <= warps):
-//   * depth unit  (one per block of 32 raw pixels): lane l owns raw pixel p0+l and reads its DPAD logits on the
-//     diagonal d = (l+k) mod DPAD -- bank = ((PX+1)*l + PX*k) mod 32 is a bijection in l because PX is a multiple of 4,
-//     so the reads are conflict free; max / exp / sum are order independent, so the softmax (encoder.py:99) is lane
-//     local; the probabilities are stored to prob[pixT][d] after the barrier.
-//   * context unit (one per 32 channels x 32 raw pixels): same diagonal; stores to ctx[pixT][c] hit bank c mod 32,
-//     conflict free for C = 64.
-// All raw values are held in registers across one __syncthreads(), so the transposes are in place.
+// Every warp takes one depth unit (16 depths x 32 raw pixels) and one or two context units (16 channels x 32 raw pixels).
+// Lane l owns raw pixel p0+l and walks its 16 values on the diagonal (l+k) mod 16: bank = (16*((l+k)&1) + l + const) mod 32
+// is a bijection in l for the reference pixel pitch (and conflict-free for any pitch that is a multiple of 32), so the raw
+// reads are conflict free; the transposed stores are at worst 2-way conflicted.  The softmax (encoder.py:99) over the
+// DPAD/16 depth units of a pixel is combined through two small shared arrays (max, then sum).  All raw values sit in
+// registers across the first barrier, so both transposes are in place.
 template <int DBLKS>
 __device__ __forceinline__ void transform_tile(const LiftParams& P, const TileLayout<DBLKS>& L, unsigned char* smem) {
     constexpr int DPAD = TileLayout<DBLKS>::DPAD;
     constexpr int PS = TileLayout<DBLKS>::PS;
+    constexpr int NWARPS = TileLayout<DBLKS>::NWARPS;
+    constexpr int NG = DPAD / 16;                           // depth units per pixel block
+    constexpr float L2E = 1.4426950408889634f;
     float* s_prob = reinterpret_cast<float*>(smem + L.off_prob);
     float* s_ctx = reinterpret_cast<float*>(smem + L.off_ctx);
+    float* s_max = reinterpret_cast<float*>(smem + L.off_red);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int PX = L.PX, hh = L.hh;
+    float* s_sum = s_max + NG * PX;
     const int n_pblk = (PX + 31) >> 5;
-    const int n_cblk = L.C >> 5;
+    const int n_punits = n_pblk * NG;
+    const int n_cunits = (L.C >> 4) * n_pblk;
 
-    const bool depth_unit = warp < n_pblk;
-    const bool ctx_unit = !depth_unit && warp < n_pblk * (1 + n_cblk);
-    const int pblk = depth_unit ? warp : (warp - n_pblk) % n_pblk;
-    const int c0 = ctx_unit ? ((warp - n_pblk) / n_pblk) * 32 : 0;
-    const int pix = pblk * 32 + lane;                       // raw pixel index row*WT + col
-    const bool active = (depth_unit || ctx_unit) && pix < PX;
-    const int pixT = active ? (pix % WT) * hh + pix / WT : 0;   // transposed pixel index col*hh + row
+    // ---- read phase ----
+    const bool p_unit = warp < n_punits;
+    const int pg = p_unit ? warp / n_pblk : 0, ppb = p_unit ? warp % n_pblk : 0;
+    const int ppix = ppb * 32 + lane;
+    const bool p_act = p_unit && ppix < PX;
+    float pv[16];
+    float mx = -INFINITY;
+    if (p_act && P.use_depth) {
+        const float* src = s_prob + (pg * 16) * PX + ppix;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int dd = (lane + k) & 15;
+            pv[k] = (pg * 16 + dd < P.D) ? src[dd * PX] : -INFINITY;
+            mx = fmaxf(mx, pv[k]);
+        }
+        s_max[pg * PX + ppix] = mx;
+    }
+    float cv[2][16];
+    int cpix[2], cc0[2];
+    bool c_act[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int u = warp + r * NWARPS;
+        c_act[r] = u < n_cunits;
+        cc0[r] = c_act[r] ? (u / n_pblk) * 16 : 0;
+        cpix[r] = (c_act[r] ? (u % n_pblk) : 0) * 32 + lane;
+        c_act[r] = c_act[r] && cpix[r] < PX;
+        if (c_act[r]) {
+            const float* src = s_ctx + cc0[r] * PX + cpix[r];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) cv[r][k] = src[((lane + k) & 15) * PX];
+        }
+    }
+    __syncthreads();      // every raw value is in registers; partial maxima published
 
-    float v[DPAD > 32 ? DPAD : 32];
-    if (depth_unit && active) {
+    // ---- context: transposed stores (overlap with the depth units' second pass) ----
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (c_act[r]) {
+            const int pixT = (cpix[r] % WT) * hh + cpix[r] / WT;
+            float* dst = s_ctx + pixT * L.C + cc0[r];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[(lane + k) & 15] = cv[r][k];
+        }
+    }
+    // ---- depth: exp and partial sums ----
+    if (p_act) {
         if (P.use_depth) {
-            float mx = -INFINITY;
+            float m = s_max[ppix];
 #pragma unroll
-            for (int k = 0; k < DPAD; ++k) {
-                int d = lane + k;
-                d = (d >= DPAD) ? d - DPAD : d;
-                v[k] = (d < P.D) ? s_prob[d * PX + pix] : -INFINITY;
-                mx = fmaxf(mx, v[k]);
-            }
+            for (int g = 1; g < NG; ++g) m = fmaxf(m, s_max[g * PX + ppix]);
+            const float m2 = m * L2E;
             float sum = 0.f;
-            const float mx2 = mx * 1.4426950408889634f;
 #pragma unroll
-            for (int k = 0; k < DPAD; ++k) {
-                // exp(x - max) as 2^(x*log2e - max*log2e): one FFMA + MUFU.EX2 (encoder.py:99); padding (-inf) gives 0
-                v[k] = exp2f(fmaf(v[k], 1.4426950408889634f, -mx2));
-                sum += v[k];
+            for (int k = 0; k < 16; ++k) {
+                pv[k] = exp2f(fmaf(pv[k], L2E, -m2));       // exp(x - max); padding (-inf) gives 0
+                sum += pv[k];
             }
-            const float inv = __fdiv_rn(1.0f, sum);
-#pragma unroll
-            for (int k = 0; k < DPAD; ++k) v[k] *= inv;
+            s_sum[pg * PX + ppix] = sum;
         } else {
 #pragma unroll
-            for (int k = 0; k < DPAD; ++k) {                                 // encoder.py:102: every depth gets ctx
-                int d = lane + k;
-                d = (d >= DPAD) ? d - DPAD : d;
-                v[k] = (d < P.D) ? 1.0f : 0.f;
-            }
+            for (int k = 0; k < 16; ++k) pv[k] = (pg * 16 + ((lane + k) & 15) < P.D) ? 1.0f : 0.f;   // encoder.py:102
         }
-    } else if (ctx_unit && active) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = s_ctx[(c0 + ((lane + k) & 31)) * PX + pix];
     }
-    __syncthreads();      // every raw value is in registers: both regions may now be overwritten
-
-    if (depth_unit && active) {
+    __syncthreads();      // partial sums published
+    if (p_act) {
+        float inv = 1.0f;
+        if (P.use_depth) {
+            float tot = s_sum[ppix];
 #pragma unroll
-        for (int k = 0; k < DPAD; ++k) {
-            int d = lane + k;
-            d = (d >= DPAD) ? d - DPAD : d;
-            s_prob[pixT * PS + d] = v[k];
+            for (int g = 1; g < NG; ++g) tot += s_sum[g * PX + ppix];
+            inv = __fdiv_rn(1.0f, tot);
         }
-    } else if (ctx_unit && active) {
+        const int pixT = (ppix % WT) * hh + ppix / WT;
+        float* dst = s_prob + pixT * PS + pg * 16;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) s_ctx[pixT * L.C + c0 + ((lane + k) & 31)] = v[k];
+        for (int k = 0; k < 16; ++k) dst[(lane + k) & 15] = pv[k] * inv;
     }
-    __syncthreads();
+    // no barrier here: the next reader of prob/ctx (the pooling loop) is behind the barriers of the rank staging
 }
 
 }  // namespace fiery
