@@ -348,6 +348,18 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline:
+            # the reference's own op chain (torch library kernels: softmax, inverse, argsort, cumsum, index_put ...) on this
+            # GPU -- the GPU-vs-GPU comparison SURVEY.md section 8d asks for next to the CPU number; baseline only
+            from oracle import lift_oracle as O
+            o_gpu = O.LiftOracle.from_config(cfg).to(dev)
+            with torch.no_grad():
+                for _ in range(2):
+                    o_gpu.lift(head_d, K_d, E_d)
+                t_ref_gpu = timed_steps(lambda: o_gpu.lift(head_d, K_d, E_d), 5)
+            line["reference_ops_on_gpu"] = {"value": frames / (float(np.mean(t_ref_gpu)) * 1e-3), "unit": "frames/s",
+                                            "ms_per_step": float(np.mean(t_ref_gpu)),
+                                            "what": "oracle/lift_oracle.py (the reference's PyTorch op chain) on CUDA tensors, "
+                                                    "torch library kernels, same inputs, 5 steps"}
             fps, sec, threads = time_cpu_reference(cfg, min(frames, args.cpu_frames), reps=args.cpu_reps)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_reps} reps of {min(frames, args.cpu_frames)} frame(s) of {cfg.name}: "

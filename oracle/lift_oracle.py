@@ -275,6 +275,13 @@ class LiftOracle:
         self.C = out_channels
         self.use_depth_distribution = use_depth_distribution
 
+    def to(self, device) -> "LiftOracle":
+        """Moves the constants so the same torch op chain runs on another device (oracle variant O2 of SURVEY.md section 8c:
+        the reference's ops executed on the GPU by torch's own library kernels -- a baseline, never the product)."""
+        self.resolution, self.start = self.resolution.to(device), self.start.to(device)
+        self.dimension, self.frustum = self.dimension.to(device), self.frustum.to(device)
+        return self
+
     @classmethod
     def from_config(cls, cfg) -> "LiftOracle":
         return cls(cfg.final_dim, cfg.downsample, cfg.out_channels, cfg.x_bound, cfg.y_bound, cfg.z_bound,
