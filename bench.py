@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--workload", default="cfg2_static_lss_b8", choices=sorted(CONFIGS))
     ap.add_argument("--layout", default="contiguous", choices=["contiguous", "channels_last"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-chunk", type=int, default=3, help="frames per upload/lift/download pipeline stage in the e2e run")
+    ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per upload/lift/download pipeline stage in the e2e run")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--cpu-reps", type=int, default=5)
     args = ap.parse_args()
