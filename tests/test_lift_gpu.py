@@ -275,3 +275,32 @@ def test_reference_call_site_signature_and_amp_head():
     assert O.normwise_error(bev16.detach().cpu(), exact16) < TOL
     bev16.sum().backward()
     assert h16.grad.dtype == torch.float16
+
+
+def test_all_points_masked_and_degenerate_calibration():
+    """Frustum entirely outside the grid -> BEV exactly zero (fiery.py:240-249 drops every point); a non-finite calibration
+    masks all points as well (long(NaN) is negative in the reference) instead of corrupting memory."""
+    cfg = CONFIGS["cfg1_tiny"]
+    dev = _dev()
+    K, E = make_calibration(cfg, seed=12)
+    head = torch.from_numpy(make_head(cfg, seed=12)).to(dev)
+    lift = LiftSplat.from_config(cfg).to(dev)
+    far = E.copy()
+    far[..., 0, 3] += 1.0e4                                   # rig 10 km ahead of the grid
+    bev = lift(head, torch.from_numpy(K).to(dev), torch.from_numpy(far).to(dev))
+    assert float(bev.abs().max()) == 0.0
+    idx, valid, pillar = lift.point_indices(torch.from_numpy(K).to(dev), torch.from_numpy(far).to(dev))
+    assert not bool(valid.any()) and bool((pillar == -1).all())
+    oracle = O.LiftOracle.from_config(cfg)
+    comb, _ = lift.compose_calibration(torch.from_numpy(K).to(dev), torch.from_numpy(far).to(dev))
+    idx_o, keep_o = oracle.point_indices(torch.from_numpy(K), torch.from_numpy(far), combined=comb.cpu())
+    assert torch.equal(idx.cpu(), idx_o) and not bool(keep_o.any())
+    bad = K.copy()
+    bad[0, 0, 0, 0] = float("nan")
+    bev = lift(head, torch.from_numpy(bad).to(dev), torch.from_numpy(E).to(dev))
+    torch.cuda.synchronize()
+    assert float(bev.abs().max()) == 0.0 and bool(torch.isfinite(bev).all())
+    # the scratch is still clean afterwards: a normal call gives the normal answer
+    good = lift(head, torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)).cpu()
+    exact = oracle.lift_exact(head.cpu(), torch.from_numpy(K), torch.from_numpy(E))
+    assert O.normwise_error(good, exact) < TOL
