@@ -303,6 +303,26 @@ def main():
     t_kernel = timed_steps(run_tiles, S)        # lift_forward_kernel alone (channel-last target)
     barrier()
 
+    # ---- the literal drop-in at fiery.py:261: VoxelsSumming on one frame's rank-sorted point features ------------------------
+    vs_extra = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from fiery_b200.geometry import VoxelsSumming
+        with torch.no_grad():
+            idx1, valid1, pillar1 = lift.point_indices(K_d[:1], E_d[:1])
+            keep1 = valid1[0]
+            ranks1 = pillar1[0][keep1].long()
+            order1 = ranks1.argsort()
+            ranks1 = ranks1[order1]
+            geo1 = idx1[0][keep1][order1]
+            feats1 = torch.randn(ranks1.numel(), cfg.out_channels, device=dev)
+            for _ in range(2):
+                VoxelsSumming.apply(feats1, geo1, ranks1)
+            t_vs = timed_steps(lambda: VoxelsSumming.apply(feats1, geo1, ranks1), 10)
+            t_cs = timed_steps(lambda: feats1.cumsum(0), 3)
+        vs_extra = {"rows": int(ranks1.numel()), "ms": float(np.mean(t_vs)), "torch_cumsum_ms": float(np.mean(t_cs)),
+                    "what": "fiery_b200.geometry.VoxelsSumming.apply (plan + segmented sum, incl. its host sync) on one frame's "
+                            "sorted (Nm, 64) features vs the torch.cumsum(0) alone that the reference's VoxelsSumming starts with"}
+
     def reduce_max(x):
         if not distributed:
             return x
@@ -347,6 +367,8 @@ def main():
                          "step_frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / peak},
             "clocks": clocks,
         }
+        if vs_extra is not None:
+            line["voxels_summing_dropin"] = vs_extra
         if not args.no_cpu_baseline:
             # the reference's own op chain (torch library kernels: softmax, inverse, argsort, cumsum, index_put ...) on this
             # GPU -- the GPU-vs-GPU comparison SURVEY.md section 8d asks for next to the CPU number; baseline only

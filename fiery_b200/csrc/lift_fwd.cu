@@ -99,18 +99,25 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
     for (int h = 0; h < hh; ++h, pp += PS, cp += L.C, mp += DBLKS, plp += DPAD) {
         const unsigned m = *mp;                       // depths of this block whose pillar differs from row h-1 (0 at h = 0)
         if (m) {
+            // usually one or two of the eight depths end a run here: test the two nibbles first
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const unsigned ended = m & (1u << j);
-                if (ended) {
-                    const int pl = plp[j];
-                    if (pl >= 0) {
-                        flush_pair(reinterpret_cast<float*>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4)),
-                                   acc[j][0], acc[j][1]);
-                        if (flags) flags[pl] = 1;
+            for (int nib = 0; nib < 2; ++nib) {
+                if (m & (0xfu << (4 * nib))) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = 4 * nib + jj;
+                        const unsigned ended = m & (1u << j);
+                        if (ended) {
+                            const int pl = plp[j];
+                            if (pl >= 0) {
+                                flush_pair(reinterpret_cast<float*>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4)),
+                                           acc[j][0], acc[j][1]);
+                                if (flags) flags[pl] = 0x0f;         // one bit per channel quarter of the layout pass
+                            }
+                        }
+                        clear_if(acc[j][0], acc[j][1], ended);     // predicated in-place reset (see clear_if)
                     }
                 }
-                clear_if(acc[j][0], acc[j][1], ended);     // predicated in-place reset (see clear_if)
             }
         }
         const float4 p0 = *reinterpret_cast<const float4*>(pp);
@@ -131,7 +138,7 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
         const int pl = plp[j];                        // plp now points at the last row
         if (pl >= 0) {
             flush_pair(reinterpret_cast<float*>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4)), acc[j][0], acc[j][1]);
-            if (flags) flags[pl] = 1;
+            if (flags) flags[pl] = 0x0f;         // one bit per channel quarter of the layout pass
         }
     }
 }
@@ -176,50 +183,51 @@ finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flag
     }
 }
 
-// Same pass, four consecutive pillars per thread: the 4 x 8-channel block is transposed in registers and written as 16-byte
-// stores (a warp covers 128 pillars = 512 contiguous bytes per channel).  The per-pillar version above is limited by the
-// LSU instruction queue (59 % "lg throttle" stalls: 64 four-byte stores per thread); this one issues a quarter of the
-// store instructions.  Needs X*Y to be a multiple of 4.
+// Same pass with 16-byte stores: a thread takes four consecutive pillars x one quarter of the channels (16), loads its
+// sixteen 16-byte pieces up front, transposes the 4 x 16 block in registers and writes 16 stores of 16 bytes; a warp covers
+// 128 pillars, i.e. 512 contiguous bytes per channel row.  Half the LSU instructions of the per-pillar kernel (which is
+// limited by its 64 four-byte stores per thread: 59 % "lg throttle" stalls) at the same thread count.  The touched byte
+// of a pillar carries one bit per channel quarter so the four quarter-blocks can clear their bit independently.
+// Needs X*Y to be a multiple of 4.
 __global__ void __launch_bounds__(FIN_THREADS)
-finalize_nchw_x4_kernel(float* __restrict__ accum, unsigned char* __restrict__ flags, float* __restrict__ bev,
-                        long long pillars, int blocks_per_frame) {
+finalize_nchw_q_kernel(float* __restrict__ accum, unsigned* __restrict__ flags32, float* __restrict__ bev,
+                       long long pillars, int blocks_per_frame) {
     constexpr int C = 64;
-    const int frame = blockIdx.x / blocks_per_frame;
-    const long long p0 = (static_cast<long long>(blockIdx.x % blocks_per_frame) * FIN_THREADS + threadIdx.x) * 4;
+    const int q = blockIdx.x & 3;                      // channel quarter
+    const int b = blockIdx.x >> 2;
+    const int frame = b / blocks_per_frame;
+    const long long p0 = (static_cast<long long>(b % blocks_per_frame) * FIN_THREADS + threadIdx.x) * 4;
     if (p0 >= pillars) return;
-    unsigned char* f = flags + static_cast<size_t>(frame) * pillars + p0;
-    const uchar4 fl = *reinterpret_cast<const uchar4*>(f);
-    const bool t0 = fl.x != 0, t1 = fl.y != 0, t2 = fl.z != 0, t3 = fl.w != 0;
-    float4* row = reinterpret_cast<float4*>(accum + (static_cast<size_t>(frame) * pillars + p0) * C);   // 4 rows of 16 float4
-    float* dst = bev + static_cast<size_t>(frame) * C * pillars + p0;
+    unsigned* fw = flags32 + (static_cast<size_t>(frame) * pillars + p0) / 4;
+    const unsigned word = __ldcg(fw) >> q;             // bit 0 of each byte: this quarter still holds data for that pillar
+    const bool t0 = word & 0x1u, t1 = word & 0x100u, t2 = word & 0x10000u, t3 = word & 0x1000000u;
+    float4* row = reinterpret_cast<float4*>(accum + (static_cast<size_t>(frame) * pillars + p0) * C) + q * 4;   // rows are 16 float4 apart
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int c8 = 0; c8 < C / 8; ++c8) {
-        float4 v[4][2];
+    float4 v[4][4];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            v[0][q] = t0 ? row[0 * 16 + c8 * 2 + q] : z4;
-            v[1][q] = t1 ? row[1 * 16 + c8 * 2 + q] : z4;
-            v[2][q] = t2 ? row[2 * 16 + c8 * 2 + q] : z4;
-            v[3][q] = t3 ? row[3 * 16 + c8 * 2 + q] : z4;
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            if (t0) row[0 * 16 + c8 * 2 + q] = z4;
-            if (t1) row[1 * 16 + c8 * 2 + q] = z4;
-            if (t2) row[2 * 16 + c8 * 2 + q] = z4;
-            if (t3) row[3 * 16 + c8 * 2 + q] = z4;
-        }
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            float* d = dst + static_cast<size_t>(c8 * 8 + q * 4) * pillars;
-            *reinterpret_cast<float4*>(d) = make_float4(v[0][q].x, v[1][q].x, v[2][q].x, v[3][q].x);
-            *reinterpret_cast<float4*>(d + pillars) = make_float4(v[0][q].y, v[1][q].y, v[2][q].y, v[3][q].y);
-            *reinterpret_cast<float4*>(d + 2 * pillars) = make_float4(v[0][q].z, v[1][q].z, v[2][q].z, v[3][q].z);
-            *reinterpret_cast<float4*>(d + 3 * pillars) = make_float4(v[0][q].w, v[1][q].w, v[2][q].w, v[3][q].w);
-        }
+    for (int k = 0; k < 4; ++k) {
+        v[0][k] = t0 ? __ldcg(row + 0 * 16 + k) : z4;
+        v[1][k] = t1 ? __ldcg(row + 1 * 16 + k) : z4;
+        v[2][k] = t2 ? __ldcg(row + 2 * 16 + k) : z4;
+        v[3][k] = t3 ? __ldcg(row + 3 * 16 + k) : z4;
     }
-    if (t0 | t1 | t2 | t3) *reinterpret_cast<uchar4*>(f) = make_uchar4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (t0) row[0 * 16 + k] = z4;
+        if (t1) row[1 * 16 + k] = z4;
+        if (t2) row[2 * 16 + k] = z4;
+        if (t3) row[3 * 16 + k] = z4;
+    }
+    float* dst = bev + (static_cast<size_t>(frame) * C + q * 16) * pillars + p0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float* d = dst + static_cast<size_t>(4 * k) * pillars;
+        *reinterpret_cast<float4*>(d) = make_float4(v[0][k].x, v[1][k].x, v[2][k].x, v[3][k].x);
+        *reinterpret_cast<float4*>(d + pillars) = make_float4(v[0][k].y, v[1][k].y, v[2][k].y, v[3][k].y);
+        *reinterpret_cast<float4*>(d + 2 * pillars) = make_float4(v[0][k].z, v[1][k].z, v[2][k].z, v[3][k].z);
+        *reinterpret_cast<float4*>(d + 3 * pillars) = make_float4(v[0][k].w, v[1][k].w, v[2][k].w, v[3][k].w);
+    }
+    if (word & 0x01010101u) atomicAnd(fw, ~(0x01010101u << q));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -328,8 +336,8 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
         if (rc != FIERY_OK) return rc;
         if (P.pillars % 4 == 0) {
             const int bpf4 = static_cast<int>((P.pillars / 4 + FIN_THREADS - 1) / FIN_THREADS);
-            finalize_nchw_x4_kernel<<<static_cast<unsigned>(bpf4) * Q.n_frames, FIN_THREADS, 0, stream>>>(
-                Q.accum, Q.touched, bev_out + static_cast<size_t>(f0) * P.C * P.pillars, P.pillars, bpf4);
+            finalize_nchw_q_kernel<<<static_cast<unsigned>(bpf4) * Q.n_frames * 4, FIN_THREADS, 0, stream>>>(
+                Q.accum, reinterpret_cast<unsigned*>(Q.touched), bev_out + static_cast<size_t>(f0) * P.C * P.pillars, P.pillars, bpf4);
         } else {
             finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * Q.n_frames, FIN_THREADS, 0, stream>>>(
                 Q.accum, Q.touched, bev_out + static_cast<size_t>(f0) * P.C * P.pillars, P.pillars, bpf);
