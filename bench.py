@@ -360,7 +360,7 @@ def main():
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(head_h.numel() * 4 + K_h.numel() * 4 + E_h.numel() * 4),
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},
-            "gpu_launches": (1 if args.layout == "channels_last" else 2) * S,
+            "gpu_launches": (1 if args.layout == "channels_last" else 4) * S,   # lift, layout pass, 2 scratch-clearing kernels
             "roofline": {"bound": "hbm", "kernel": "lift_forward_kernel", "achieved": achieved, "peak": peak,
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "lift_plus_finalize_ms": ms_both,
