@@ -215,10 +215,11 @@ finalize_nchw_q_kernel(float* __restrict__ accum, unsigned* __restrict__ flags32
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         float* d = dst + static_cast<size_t>(4 * k) * pillars;
-        *reinterpret_cast<float4*>(d) = make_float4(v[0][k].x, v[1][k].x, v[2][k].x, v[3][k].x);
-        *reinterpret_cast<float4*>(d + pillars) = make_float4(v[0][k].y, v[1][k].y, v[2][k].y, v[3][k].y);
-        *reinterpret_cast<float4*>(d + 2 * pillars) = make_float4(v[0][k].z, v[1][k].z, v[2][k].z, v[3][k].z);
-        *reinterpret_cast<float4*>(d + 3 * pillars) = make_float4(v[0][k].w, v[1][k].w, v[2][k].w, v[3][k].w);
+        // streaming stores: the BEV is written once and not re-read here; keep L2 for the accumulator rows
+        __stcs(reinterpret_cast<float4*>(d), make_float4(v[0][k].x, v[1][k].x, v[2][k].x, v[3][k].x));
+        __stcs(reinterpret_cast<float4*>(d + pillars), make_float4(v[0][k].y, v[1][k].y, v[2][k].y, v[3][k].y));
+        __stcs(reinterpret_cast<float4*>(d + 2 * pillars), make_float4(v[0][k].z, v[1][k].z, v[2][k].z, v[3][k].z));
+        __stcs(reinterpret_cast<float4*>(d + 3 * pillars), make_float4(v[0][k].w, v[1][k].w, v[2][k].w, v[3][k].w));
     }
 }
 
