@@ -37,6 +37,17 @@ METRIC = "camera->BEV lift frames/sec (6-cam 224x480 -> 200x200)"
 L2_FLUSH_BYTES = 256 << 20
 
 
+def load_traffic(workload: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload (profiles/traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as fh:
+            v = json.load(fh).get(workload)
+        return int(v) if v is not None else None
+    except (OSError, ValueError):
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -362,7 +373,7 @@ def main():
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},
             "gpu_launches": (1 if args.layout == "channels_last" else 4) * S,   # lift, layout pass, 2 scratch-clearing kernels
             "roofline": {"bound": "hbm", "kernel": "lift_forward_kernel", "achieved": achieved, "peak": peak,
-                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(cfg.name),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "lift_plus_finalize_ms": ms_both,
                          "step_frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / peak},
             "clocks": clocks,
