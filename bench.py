@@ -334,6 +334,26 @@ def main():
                     "what": "fiery_b200.geometry.VoxelsSumming.apply (plan + segmented sum, incl. its host sync) on one frame's "
                             "sorted (Nm, 64) features vs the torch.cumsum(0) alone that the reference's VoxelsSumming starts with"}
 
+    # ---- next row of the path: cumulative_warp_features on the lifted BEV (b=3 samples x s=3 steps) ---------
+    warp_extra = None
+    if rank == 0:
+        from fiery_b200.warp import cumulative_warp_features
+        from fiery_b200.synthetic import make_egomotion
+        wb, ws = 3, 3
+        xw = torch.randn(wb, ws, cfg.out_channels, X, Y, device=dev)
+        fl = torch.from_numpy(make_egomotion(wb, ws, seed=7)).to(dev)
+        ext = (float(cfg.x_bound[1]), float(cfg.y_bound[1]))
+        with torch.no_grad():
+            for _ in range(3):
+                cumulative_warp_features(xw, fl, mode="bilinear", spatial_extent=ext)
+            t_w = timed_steps(lambda: cumulative_warp_features(xw, fl, mode="bilinear", spatial_extent=ext), S)
+        w_bytes = 2 * xw.numel() * 4                                    # read every frame once + write every frame once
+        w_ms = float(np.mean(t_w))
+        warp_extra = {"frames": wb * ws, "ms_per_call": w_ms, "frames_per_s": wb * ws / (w_ms * 1e-3),
+                      "algorithmic_bytes": w_bytes, "achieved_gbs": w_bytes / (w_ms * 1e-3) / 1e9,
+                      "what": "fiery_b200.warp.cumulative_warp_features (pose algebra in torch + one warp kernel launch), "
+                              "(3, 3, 64, X, Y) fp32, eager call incl. its small torch ops"}
+
     def reduce_max(x):
         if not distributed:
             return x
@@ -380,6 +400,10 @@ def main():
         }
         if vs_extra is not None:
             line["voxels_summing_dropin"] = vs_extra
+        if warp_extra is not None:
+            peak_w, _ = load_peaks()
+            warp_extra["frac_of_hbm_peak"] = warp_extra["achieved_gbs"] / peak_w
+            line["next_row_cumulative_warp"] = warp_extra
         if not args.no_cpu_baseline:
             # the reference's own op chain (torch library kernels: softmax, inverse, argsort, cumsum, index_put ...) on this
             # GPU -- the GPU-vs-GPU comparison SURVEY.md section 8d asks for next to the CPU number; baseline only

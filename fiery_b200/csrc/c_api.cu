@@ -82,6 +82,8 @@ int lift_chunk_frames(int n_frames, long long pillars, int channels);
 int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, float* workspace, cudaStream_t);
 int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t);
 int launch_compose(int n, const float* K, const float* E, float* combined, float* translation, cudaStream_t);
+int launch_warp(int forward, int n_maps, int C, int H, int W, const float* a, long long a_stride, const float* theta,
+                const unsigned char* copy_mask, float* b, long long b_stride, int nearest, cudaStream_t stream);
 int vs_plan(int64_t n_rows, const int64_t* ranks, int32_t* seg, int64_t* host_n, cudaStream_t);
 int vs_forward(int64_t n_rows, int channels, int64_t feat_stride, const float* feats, const int64_t* coords,
                const int32_t* seg, int64_t n_seg, float* sums, int64_t* coords_out, cudaStream_t);
@@ -207,6 +209,24 @@ FIERY_API int fiery_voxels_summing_backward(int64_t n_rows, int32_t channels, co
     if (n_rows == 0) return FIERY_OK;
     FIERY_REQUIRE(grad_sums && segment_of_row && grad_feats, "NULL pointer");
     return vs_backward(n_rows, channels, grad_sums, segment_of_row, grad_feats, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_warp_features_forward(int32_t n_maps, int32_t channels, int32_t height, int32_t width, const float* x,
+                                          int64_t x_map_stride, const float* theta, const uint8_t* copy_mask, float* out,
+                                          int64_t out_map_stride, int32_t nearest, void* stream) {
+    FIERY_REQUIRE(n_maps >= 0 && channels >= 1 && height >= 1 && width >= 1, "warp: bad shape");
+    FIERY_REQUIRE(n_maps == 0 || (x && theta && out), "warp: NULL pointer");
+    return launch_warp(1, n_maps, channels, height, width, x, x_map_stride, theta, copy_mask, out, out_map_stride, nearest ? 1 : 0,
+                       static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_warp_features_backward(int32_t n_maps, int32_t channels, int32_t height, int32_t width, const float* grad_out,
+                                           int64_t grad_out_map_stride, const float* theta, const uint8_t* copy_mask,
+                                           float* grad_x, int64_t grad_x_map_stride, int32_t nearest, void* stream) {
+    FIERY_REQUIRE(n_maps >= 0 && channels >= 1 && height >= 1 && width >= 1, "warp: bad shape");
+    FIERY_REQUIRE(n_maps == 0 || (grad_out && theta && grad_x), "warp: NULL pointer");
+    return launch_warp(0, n_maps, channels, height, width, grad_out, grad_out_map_stride, theta, copy_mask, grad_x, grad_x_map_stride,
+                       nearest ? 1 : 0, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -160,3 +160,17 @@ def shard_frames(n_frames: int, world_size: int, rank: int) -> range:
     base, rem = divmod(n_frames, world_size)
     start = rank * base + min(rank, rem)
     return range(start, start + base + (1 if rank < rem else 0))
+
+
+def make_egomotion(batch: int, steps: int, seed: int = 0) -> np.ndarray:
+    """``future_egomotion (b, s, 6)`` as fiery/data.py:350-363 provides it: per-step 6-DoF ego motion (tx, ty, tz, rx, ry, rz).
+    Driving-like: ~0.5 s between frames at 5-15 m/s forward, small lateral slip, yaw rate up to ~0.2 rad/step."""
+    rng = np.random.default_rng(seed + 3000017)
+    v = np.zeros((batch, steps, 6), dtype=np.float32)
+    v[..., 0] = rng.uniform(2.5, 7.5, (batch, steps))
+    v[..., 1] = rng.normal(0.0, 0.2, (batch, steps))
+    v[..., 2] = rng.normal(0.0, 0.02, (batch, steps))
+    v[..., 3] = rng.normal(0.0, 0.005, (batch, steps))
+    v[..., 4] = rng.normal(0.0, 0.005, (batch, steps))
+    v[..., 5] = rng.normal(0.0, 0.08, (batch, steps))
+    return v

@@ -1,0 +1,145 @@
+"""BEV feature warping behind the reference's signatures.
+
+Mirrors, same names / arguments / return values:
+  * ``warp_features(x, flow, mode='nearest', spatial_extent=None)``              fiery/utils/geometry.py:181-222
+  * ``cumulative_warp_features(x, flow, mode='nearest', spatial_extent=None)``   fiery/utils/geometry.py:225-253
+    (call site fiery/models/fiery.py:143-146 with ``mode='bilinear'``)
+and the pose helpers they use (``pose_vec2mat`` :145-160, ``euler2mat`` :110-142, ``mat2pose_vec`` :82-107).
+
+The 6-DoF pose algebra (a few 4x4 matrices) is evaluated with the same torch calls as the reference on the inputs' device;
+the sampling itself -- ``affine_grid`` + ``grid_sample`` over the (b, C, X, Y) feature maps, 10 MB per frame each way -- runs
+in ``warp_forward_kernel`` / ``warp_backward_kernel`` (fiery_b200/csrc/warp.cu) through the C ABI.  One launch warps all past
+frames of a sequence straight into the output tensor; the present frame is copied.  No CPU path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .geometry import _require_cuda, _stream_ptr
+
+
+def euler2mat(angle: torch.Tensor) -> torch.Tensor:
+    """(..., 3) Euler angles -> (..., 3, 3) rotation = Rx @ Ry @ Rz; geometry.py:110-142."""
+    shape = angle.shape
+    a = angle.reshape(-1, 3)
+    x, y, z = a[:, 0], a[:, 1], a[:, 2]
+    zeros, ones = torch.zeros_like(z), torch.ones_like(z)
+    cosz, sinz = torch.cos(z), torch.sin(z)
+    zmat = torch.stack([cosz, -sinz, zeros, sinz, cosz, zeros, zeros, zeros, ones], dim=1).view(-1, 3, 3)
+    cosy, siny = torch.cos(y), torch.sin(y)
+    ymat = torch.stack([cosy, zeros, siny, zeros, ones, zeros, -siny, zeros, cosy], dim=1).view(-1, 3, 3)
+    cosx, sinx = torch.cos(x), torch.sin(x)
+    xmat = torch.stack([ones, zeros, zeros, zeros, cosx, -sinx, zeros, sinx, cosx], dim=1).view(-1, 3, 3)
+    return xmat.bmm(ymat).bmm(zmat).view(*shape[:-1], 3, 3)
+
+
+def pose_vec2mat(vec: torch.Tensor) -> torch.Tensor:
+    """(..., 6) (tx, ty, tz, rx, ry, rz) -> (..., 4, 4); geometry.py:145-160."""
+    rot_mat = euler2mat(vec[..., 3:].contiguous())
+    transform = torch.cat([rot_mat, vec[..., :3].unsqueeze(-1)], dim=-1)
+    transform = F.pad(transform, [0, 0, 0, 1], value=0)
+    transform[..., 3, 3] = 1.0
+    return transform
+
+
+def mat2pose_vec(matrix: torch.Tensor) -> torch.Tensor:
+    """(..., 4, 4) -> (..., 6); geometry.py:82-107."""
+    rotx = torch.atan2(-matrix[..., 1, 2], matrix[..., 2, 2])
+    cosy = torch.sqrt(matrix[..., 1, 2] ** 2 + matrix[..., 2, 2] ** 2)
+    roty = torch.atan2(matrix[..., 0, 2], cosy)
+    rotz = torch.atan2(-matrix[..., 0, 1], matrix[..., 0, 0])
+    return torch.cat((matrix[..., :3, 3], torch.stack((rotx, roty, rotz), dim=-1)), dim=-1)
+
+
+def _theta(flow: torch.Tensor, spatial_extent) -> torch.Tensor:
+    """The (b, 2, 3) affine map of warp_features: z-rotation + normalised xy translation; geometry.py:197-219."""
+    angle = flow[:, 5].clone()
+    translation = flow[:, :2].clone()
+    translation[:, 0] /= spatial_extent[0]
+    translation[:, 1] /= spatial_extent[1]
+    translation[:, 0] *= -1
+    cos_theta, sin_theta = torch.cos(angle), torch.sin(angle)
+    return torch.stack([cos_theta, -sin_theta, translation[:, 1], sin_theta, cos_theta, translation[:, 0]], dim=-1).view(-1, 2, 3)
+
+
+def _mode_flag(mode: str) -> int:
+    if mode == "bilinear":
+        return 0
+    if mode == "nearest":
+        return 1
+    raise ValueError(f"mode must be 'bilinear' or 'nearest', got {mode!r}")
+
+
+def _dense_maps(t: torch.Tensor) -> torch.Tensor:
+    """(n, C, H, W) float32 with dense channel planes (any map stride)."""
+    n, C, H, W = t.shape
+    if t.dtype == torch.float32 and t.stride(3) == 1 and t.stride(2) == W and t.stride(1) == H * W:
+        return t
+    return t.float().contiguous()
+
+
+class _WarpMaps(torch.autograd.Function):
+    """x (n, C, H, W) sampled under theta (n, 2, 3); maps flagged in ``copy_mask`` (n,) uint8 pass through unchanged."""
+
+    @staticmethod
+    def forward(ctx, x, theta, copy_mask, nearest: int):
+        _require_cuda(x, "x")
+        lib = _lib.load()
+        n, C, H, W = x.shape
+        xs = _dense_maps(x)
+        th = theta.detach().float().contiguous()
+        out = torch.empty((n, C, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.fiery_warp_features_forward(n, C, H, W, xs.data_ptr(), xs.stride(0) if n else 0, th.data_ptr(),
+                                                       copy_mask.data_ptr() if copy_mask is not None else 0, out.data_ptr(),
+                                                       C * H * W, nearest, _stream_ptr(x.device)), "fiery_warp_features_forward")
+        ctx.save_for_backward(th, copy_mask if copy_mask is not None else torch.empty(0, dtype=torch.uint8, device=x.device))
+        ctx.has_mask = copy_mask is not None
+        ctx.nearest, ctx.shape, ctx.dtype = nearest, tuple(x.shape), x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        th, mask = ctx.saved_tensors
+        lib = _lib.load()
+        n, C, H, W = ctx.shape
+        g = _dense_maps(grad_out)
+        grad_x = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(lib.fiery_warp_features_backward(n, C, H, W, g.data_ptr(), g.stride(0) if n else 0, th.data_ptr(),
+                                                        mask.data_ptr() if ctx.has_mask else 0, grad_x.data_ptr(), C * H * W,
+                                                        ctx.nearest, _stream_ptr(g.device)), "fiery_warp_features_backward")
+        return grad_x.to(ctx.dtype), None, None, None
+
+
+def warp_features(x: torch.Tensor, flow, mode: str = "nearest", spatial_extent=None) -> torch.Tensor:
+    """Applies a z-rotation and xy translation to the feature map ``x (b, c, h, w)``; ``flow (b, 6)``; geometry.py:181-222."""
+    if flow is None:
+        return x
+    res = _WarpMaps.apply(x, _theta(flow, spatial_extent), None, _mode_flag(mode))
+    return res if x.dtype == torch.float32 else res.to(x.dtype)
+
+
+def cumulative_warp_features(x: torch.Tensor, flow: torch.Tensor, mode: str = "nearest", spatial_extent=None) -> torch.Tensor:
+    """Warps a sequence ``x (b, t, c, h, w)`` by accumulating incremental egomotion ``flow (b, t, 6)``: x[:, -1] stays, x[:, t]
+    is warped with flow[:, t] @ ... @ flow[:, -2]; geometry.py:225-253.  ONE kernel launch produces the whole result (past
+    frames sampled, present frame copied); the reference clones x, warps frame by frame and stacks."""
+    b, T = x.shape[:2]
+    if T == 1:
+        return x
+    _require_cuda(x, "x")
+    mats = pose_vec2mat(flow)                                                  # geometry.py:241
+    thetas = [None] * T
+    cum_flow = mats[:, -2]
+    for t in reversed(range(T - 1)):                                           # geometry.py:244-251
+        thetas[t] = _theta(mat2pose_vec(cum_flow), spatial_extent)
+        cum_flow = mats[:, t - 1] @ cum_flow
+    thetas[T - 1] = torch.zeros_like(thetas[0])                                # present frame: copied, theta unused
+    theta = torch.stack(thetas, 1).reshape(b * T, 2, 3)
+    copy_mask = torch.zeros((b, T), dtype=torch.uint8, device=x.device)
+    copy_mask[:, -1] = 1
+    xm = x.reshape(b * T, *x.shape[2:])
+    res = _WarpMaps.apply(xm, theta, copy_mask.reshape(-1), _mode_flag(mode)).view(x.shape)
+    return res if x.dtype == torch.float32 else res.to(x.dtype)

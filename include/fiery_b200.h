@@ -16,6 +16,9 @@
  *       exposes the integer voxel coordinates the reference computes at fiery.py:236-256 (for parity checks)
  *   fiery_compose_calibration
  *       exposes combined = R @ inverse(K), translation  (fiery.py:196,203)
+ *   fiery_warp_features_forward / _backward
+ *       replace affine_grid + grid_sample inside warp_features  fiery/utils/geometry.py:219-220 (called from
+ *       cumulative_warp_features geometry.py:225-253, call site fiery.py:143)   [SURVEY.md section 8f, next-1]
  *
  * Conventions: every pointer is a DEVICE pointer on the current CUDA device unless its name starts with
  * `host_`; tensors are dense row-major with the shapes given; `stream` is a cudaStream_t passed as void*
@@ -142,6 +145,22 @@ FIERY_API int fiery_voxels_summing_forward(int64_t n_rows, int32_t channels, int
                                  float* sums_out, int64_t* coords_out, void* stream);
 FIERY_API int fiery_voxels_summing_backward(int64_t n_rows, int32_t channels, const float* grad_sums,
                                   const int32_t* segment_of_row, float* grad_feats, void* stream);
+
+/*
+ * BEV feature warping -- the heavy part of warp_features / cumulative_warp_features (fiery/utils/geometry.py:181-253, call
+ * site fiery/models/fiery.py:143-146): affine_grid + grid_sample (align_corners=False, zero padding; bilinear, or nearest
+ * if `nearest` != 0) of n_maps feature maps (C, H, W) fp32 under the affine maps theta (n_maps, 2, 3).  Map m starts at
+ * x + m * x_map_stride (elements); channel planes are dense (H*W).  copy_mask (n_maps bytes, may be NULL): maps with a
+ * non-zero byte are copied unchanged -- the present frame of a sequence (geometry.py:243).  The pose algebra that yields
+ * theta is tiny and stays with the caller (fiery_b200/warp.py mirrors geometry.py:197-219, 241-251).
+ * backward: grad_x[m] += adjoint of the sampling applied to grad_out[m]; grad_x must be zero-filled (or hold a running sum).
+ */
+FIERY_API int fiery_warp_features_forward(int32_t n_maps, int32_t channels, int32_t height, int32_t width, const float* x,
+                                          int64_t x_map_stride, const float* theta, const uint8_t* copy_mask, float* out,
+                                          int64_t out_map_stride, int32_t nearest, void* stream);
+FIERY_API int fiery_warp_features_backward(int32_t n_maps, int32_t channels, int32_t height, int32_t width, const float* grad_out,
+                                           int64_t grad_out_map_stride, const float* theta, const uint8_t* copy_mask,
+                                           float* grad_x, int64_t grad_x_map_stride, int32_t nearest, void* stream);
 
 #ifdef __cplusplus
 }

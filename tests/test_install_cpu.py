@@ -18,9 +18,15 @@ def fake_fiery(tmp_path, monkeypatch):
     (root / "utils" / "geometry.py").write_text(textwrap.dedent("""
         class VoxelsSumming:            # stands for fiery/utils/geometry.py:283
             tag = "reference"
+
+        def warp_features(x, flow, mode='nearest', spatial_extent=None):              # geometry.py:181
+            return "reference"
+
+        def cumulative_warp_features(x, flow, mode='nearest', spatial_extent=None):   # geometry.py:225
+            return "reference"
     """))
     (root / "models" / "fiery.py").write_text(textwrap.dedent("""
-        from fiery.utils.geometry import VoxelsSumming          # bound at import, like fiery/models/fiery.py:10
+        from fiery.utils.geometry import cumulative_warp_features, VoxelsSumming          # bound at import, like fiery/models/fiery.py:10
 
         class Fiery:
             def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):   # fiery.py:275
@@ -48,7 +54,11 @@ def test_install_rebinds_and_uninstall_restores(fake_fiery):
     assert fiery_mod.Fiery.calculate_birds_eye_view_features is ref_bev
     fb.install()                                                                    # level="fused"
     assert fiery_mod.Fiery.calculate_birds_eye_view_features is ours_bev
+    fb.install(level="all")
+    from fiery_b200.warp import cumulative_warp_features as ours_cwf
+    assert fiery_mod.cumulative_warp_features is ours_cwf and geometry.cumulative_warp_features is ours_cwf
     fb.uninstall()
+    assert fiery_mod.cumulative_warp_features is not ours_cwf and geometry.cumulative_warp_features("x", None) == "reference"
     assert geometry.VoxelsSumming is ref_vs and fiery_mod.VoxelsSumming is ref_vs
     assert fiery_mod.Fiery.calculate_birds_eye_view_features is ref_bev
     with pytest.raises(ValueError):

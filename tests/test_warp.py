@@ -1,0 +1,101 @@
+"""cumulative_warp_features / warp_features (fiery/utils/geometry.py:181-253).
+CPU: the oracle reproduces the reference's recorded outputs.  GPU: the CUDA path (C ABI) matches the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from fiery_b200.synthetic import make_egomotion
+from oracle import warp_oracle as W
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "warp.npz")
+TOL = 1e-4       # north_star: fp32 features within 1e-4 relative
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+@pytest.mark.parametrize("tag", ["small", "rect"])
+def test_oracle_matches_reference(golden, tag):
+    x = torch.from_numpy(golden[f"{tag}__x"]).requires_grad_(True)
+    flow = torch.from_numpy(golden[f"{tag}__flow"])
+    extent = tuple(float(v) for v in golden[f"{tag}__extent"])
+    out = W.cumulative_warp_features(x.clone(), flow, mode="bilinear", spatial_extent=extent)
+    assert torch.allclose(out.detach(), torch.from_numpy(golden[f"{tag}__ref"]), rtol=1e-6, atol=1e-6)
+    out.backward(torch.from_numpy(golden[f"{tag}__gout"]))
+    assert torch.allclose(x.grad, torch.from_numpy(golden[f"{tag}__grad"]), rtol=1e-5, atol=1e-6)
+    assert torch.equal(out[:, -1].detach(), x[:, -1].detach())            # present frame untouched (geometry.py:243)
+
+
+def test_oracle_single_frame_is_identity():
+    x = torch.randn(2, 1, 3, 8, 8)
+    assert W.cumulative_warp_features(x, torch.zeros(2, 1, 6), mode="bilinear", spatial_extent=(50.0, 50.0)) is x
+
+
+def _gpu_case(golden, tag):
+    b, t, c, h, w = (int(v) for v in golden[f"{tag}__shape"])
+    flow = torch.from_numpy(golden[f"{tag}__flow"])
+    extent = tuple(float(v) for v in golden[f"{tag}__extent"])
+    if f"{tag}__x" in golden.files:
+        x = torch.from_numpy(golden[f"{tag}__x"])
+    else:
+        torch.manual_seed(0)                                            # same random stream as oracle/gen_golden_warp.py:
+        xs = {}                                                         # per case x = randn(shape), then gout = randn(shape)
+        for tg, shp in (("small", (2, 3, 5, 12, 16)), ("rect", (1, 4, 3, 20, 10)), ("bev", (1, 3, 8, 200, 200))):
+            xs[tg] = torch.randn(*shp)
+            torch.randn(*shp)
+        x = xs[tag]
+    return x, flow, extent
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["small", "rect", "bev"])
+def test_gpu_matches_oracle_and_reference(golden, tag):
+    from fiery_b200.warp import cumulative_warp_features, warp_features
+    dev = torch.device("cuda:0")
+    x, flow, extent = _gpu_case(golden, tag)
+    xd = x.to(dev).requires_grad_(True)
+    out = cumulative_warp_features(xd, flow.to(dev), mode="bilinear", spatial_extent=extent)
+    assert out.shape == x.shape and out.dtype == torch.float32
+    xo = x.clone().requires_grad_(True)
+    ref = W.cumulative_warp_features(xo.clone(), flow, mode="bilinear", spatial_extent=extent)
+    scale = float(ref.abs().max())
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) <= TOL * scale
+    assert torch.equal(out[:, -1].detach().cpu(), x[:, -1])                # present frame bit-exact
+    gout = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+    out.backward(gout.to(dev))
+    ref.backward(gout)
+    gscale = float(xo.grad.abs().max())
+    assert float((xd.grad.cpu() - xo.grad).abs().max()) <= TOL * gscale
+    if f"{tag}__ref_at_pick" in golden.files:                              # the reference's own recorded samples
+        pick = golden[f"{tag}__pick"]
+        assert np.abs(out.detach().cpu().flatten()[pick].numpy() - golden[f"{tag}__ref_at_pick"]).max() <= TOL * scale
+    # single-map entry point, both sampling modes
+    for mode in ("bilinear", "nearest"):
+        one = warp_features(x[:, 0].to(dev), flow[:, 0].to(dev), mode=mode, spatial_extent=extent).cpu()
+        ref1 = W.warp_features(x[:, 0], flow[:, 0], mode=mode, spatial_extent=extent)
+        if mode == "bilinear":
+            assert float((one - ref1).abs().max()) <= TOL * scale
+        else:       # nearest: a 1-ulp coordinate difference may flip a pick exactly between two pixels; allow a handful
+            assert float(((one - ref1).abs() > TOL * scale).float().mean()) < 1e-3
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_properties():
+    """Full benchmark size (3 x 3 frames of 64 x 200 x 200): zero ego motion is the identity up to fp32 rounding of the
+    sample positions; the warp is linear in x."""
+    from fiery_b200.warp import cumulative_warp_features
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 3, 64, 200, 200, generator=g).to(dev)
+    y = torch.randn(3, 3, 64, 200, 200, generator=g).to(dev)
+    still = cumulative_warp_features(x, torch.zeros(3, 3, 6, device=dev), mode="bilinear", spatial_extent=(50.0, 50.0))
+    assert float((still - x).abs().max()) < 1e-3
+    flow = torch.from_numpy(make_egomotion(3, 3, seed=2)).to(dev)
+    a = cumulative_warp_features(x, flow, mode="bilinear", spatial_extent=(50.0, 50.0))
+    b = cumulative_warp_features(y, flow, mode="bilinear", spatial_extent=(50.0, 50.0))
+    c = cumulative_warp_features(0.5 * x + y, flow, mode="bilinear", spatial_extent=(50.0, 50.0))
+    assert float((0.5 * a + b - c).abs().max()) < 1e-4 * float(c.abs().max())
