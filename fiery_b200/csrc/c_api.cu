@@ -84,6 +84,8 @@ int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_o
 int launch_compose(int n, const float* K, const float* E, float* combined, float* translation, cudaStream_t);
 int launch_warp(int forward, int n_maps, int C, int H, int W, const float* a, long long a_stride, const float* theta,
                 const unsigned char* copy_mask, float* b, long long b_stride, int nearest, cudaStream_t stream);
+int launch_warp_theta(int n_seq, int T, int cumulative, const float* flow, float ex, float ey, float* theta,
+                      unsigned char* copy_mask, cudaStream_t stream);
 int vs_plan(int64_t n_rows, const int64_t* ranks, int32_t* seg, int64_t* host_n, cudaStream_t);
 int vs_forward(int64_t n_rows, int channels, int64_t feat_stride, const float* feats, const int64_t* coords,
                const int32_t* seg, int64_t n_seg, float* sums, int64_t* coords_out, cudaStream_t);
@@ -227,6 +229,14 @@ FIERY_API int fiery_warp_features_backward(int32_t n_maps, int32_t channels, int
     FIERY_REQUIRE(n_maps == 0 || (grad_out && theta && grad_x), "warp: NULL pointer");
     return launch_warp(0, n_maps, channels, height, width, grad_out, grad_out_map_stride, theta, copy_mask, grad_x, grad_x_map_stride,
                        nearest ? 1 : 0, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_warp_theta(int32_t n_sequences, int32_t T, int32_t cumulative, const float* flow, float spatial_extent_x,
+                               float spatial_extent_y, float* theta, uint8_t* copy_mask, void* stream) {
+    FIERY_REQUIRE(n_sequences >= 0 && (!cumulative || T >= 1), "warp_theta: bad shape");
+    FIERY_REQUIRE(n_sequences == 0 || (flow && theta && (copy_mask || !cumulative)), "warp_theta: NULL pointer");
+    return launch_warp_theta(n_sequences, T, cumulative ? 1 : 0, flow, spatial_extent_x, spatial_extent_y, theta, copy_mask,
+                             static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -36,6 +36,12 @@ __device__ __forceinline__ void flush_pair(float* dst, unsigned long long lo, un
     red_add_v4(dst, a, b, c, d);
 }
 
+// the same under a predicate (straight-line code: run ends are tested warp-uniformly, the half-warp that owns the run flushes)
+__device__ __forceinline__ void flush_pair_if(char* dst, unsigned long long lo, unsigned long long hi, unsigned bit) {
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 a, b, c, d;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.b64 {a, b}, %1;\n\tmov.b64 {c, d}, %2;\n\t"
+                 "@p red.global.add.v4.f32 [%0], {a, b, c, d};\n\t}" :: "l"(dst), "l"(lo), "l"(hi), "r"(bit) : "memory");
+}
+
 template <int DBLKS>
 __global__ void __launch_bounds__(64 * DBLKS, 2)
 lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams P) {
@@ -70,52 +76,48 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
     transform_tile<DBLKS>(P, L, smem);                // softmax + transposes (two barriers inside; camera visible after)
     stage_pillars<DBLKS>(P, L, smem, w0);
     __syncthreads();
-    stage_change_bits<DBLKS>(L, smem);
+    stage_events<DBLKS>(L, smem, P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr);
     __syncthreads();
 
     // ---- pooling: thread = (column wt, depth block dblk of 8, channel group cg of 4) ----------------------------------
-    const int unit = warp * 2 + (lane >> 4);
+    const int half = lane >> 4;
+    const int unit = warp * 2 + half;
     const int wt = unit / DBLKS, dblk = unit % DBLKS;
     const int cg = lane & 15;
     const int hh = L.hh;
     const float* prob = reinterpret_cast<const float*>(smem + L.off_prob) + (wt * hh) * PS + dblk * 8;
     const float* ctx = reinterpret_cast<const float*>(smem + L.off_ctx) + (wt * hh) * L.C + cg * 4;
     const int* pillar = reinterpret_cast<const int*>(smem + L.off_pillar) + (wt * hh) * DPAD + dblk * 8;
-    const unsigned char* chg = smem + L.off_chg + (wt * hh) * DBLKS + dblk;
     char* out = reinterpret_cast<char*>(P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cg * 4);
-    unsigned char* flags = (P.touched && cg == 0) ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
+    // lane r keeps the warp's event word of row r; every row broadcasts its word, so all run-end branches below are
+    // warp-uniform (the two half-warps own different depths and would otherwise diverge on every event)
+    const unsigned ev_mine = reinterpret_cast<const unsigned*>(smem + L.off_ev)[warp * 32 + lane];
+    const unsigned own_shift = 8 * half;
 
     unsigned long long acc[8][2];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j][0] = acc[j][1] = 0ull;
 
-    // Rows in lockstep.  Pillar changes are frequent at warp level (16 depths share a warp: ~11 of 28 rows see a change
-    // somewhere with a 1-degree camera roll), so the per-row cost of looking is kept to one byte load and a branch.
     const float* pp = prob;
     const float* cp = ctx;
-    const unsigned char* mp = chg;
     const int* plp = pillar - DPAD;                  // row h-1
 #pragma unroll 2
-    for (int h = 0; h < hh; ++h, pp += PS, cp += L.C, mp += DBLKS, plp += DPAD) {
-        const unsigned m = *mp;                       // depths of this block whose pillar differs from row h-1 (0 at h = 0)
-        if (m) {
-            // usually one or two of the eight depths end a run here: test the two nibbles first
+    for (int h = 0; h < hh; ++h, pp += PS, cp += L.C, plp += DPAD) {
+        const unsigned ev = __shfl_sync(0xffffffffu, ev_mine, h);
+        const unsigned mw = (ev | (ev >> 8)) & 0xffu;                // depth slots that end a run in either half-warp
+        if (mw) {
+            const unsigned own = ev >> own_shift;                     // bits 0-7: my runs that end, bits 16-23: ... and flush
 #pragma unroll
             for (int nib = 0; nib < 2; ++nib) {
-                if (m & (0xfu << (4 * nib))) {
+                if (mw & (0xfu << (4 * nib))) {
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = 4 * nib + jj;
-                        const unsigned ended = m & (1u << j);
-                        if (ended) {
-                            const int pl = plp[j];
-                            if (pl >= 0) {
-                                flush_pair(reinterpret_cast<float*>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4)),
-                                           acc[j][0], acc[j][1]);
-                                if (flags) flags[pl] = 0x0f;         // one bit per channel quarter of the layout pass
-                            }
+                        if (mw & (1u << j)) {
+                            const unsigned pl = static_cast<unsigned>(plp[j]);
+                            flush_pair_if(out + static_cast<size_t>(pl) * (64 * 4), acc[j][0], acc[j][1], own & (0x10000u << j));
+                            clear_if(acc[j][0], acc[j][1], own & (1u << j));
                         }
-                        clear_if(acc[j][0], acc[j][1], ended);     // predicated in-place reset (see clear_if)
                     }
                 }
             }
@@ -136,10 +138,7 @@ lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int pl = plp[j];                        // plp now points at the last row
-        if (pl >= 0) {
-            flush_pair(reinterpret_cast<float*>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4)), acc[j][0], acc[j][1]);
-            if (flags) flags[pl] = 0x0f;         // one bit per channel quarter of the layout pass
-        }
+        flush_pair_if(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4), acc[j][0], acc[j][1], pl >= 0 ? 1u : 0u);
     }
 }
 

@@ -6,10 +6,11 @@ Mirrors, same names / arguments / return values:
     (call site fiery/models/fiery.py:143-146 with ``mode='bilinear'``)
 and the pose helpers they use (``pose_vec2mat`` :145-160, ``euler2mat`` :110-142, ``mat2pose_vec`` :82-107).
 
-The 6-DoF pose algebra (a few 4x4 matrices) is evaluated with the same torch calls as the reference on the inputs' device;
-the sampling itself -- ``affine_grid`` + ``grid_sample`` over the (b, C, X, Y) feature maps, 10 MB per frame each way -- runs
-in ``warp_forward_kernel`` / ``warp_backward_kernel`` (fiery_b200/csrc/warp.cu) through the C ABI.  One launch warps all past
-frames of a sequence straight into the output tensor; the present frame is copied.  No CPU path.
+Two launches per call through the C ABI (fiery_b200/csrc/warp.cu): ``warp_theta_kernel`` evaluates the 6-DoF pose algebra
+(one thread per sequence, a few 4x4 matrices) and ``warp_forward_kernel`` does the sampling -- ``affine_grid`` +
+``grid_sample`` over the (b, C, X, Y) feature maps, 10 MB per frame each way -- for all past frames of a sequence straight
+into the output tensor; the present frame is copied.  The pose helpers below are the torch restatements kept for users of
+those names (``pose_vec2mat`` etc. are public in the reference); the warps do not call them.  No CPU path.
 """
 from __future__ import annotations
 
@@ -114,32 +115,42 @@ class _WarpMaps(torch.autograd.Function):
         return grad_x.to(ctx.dtype), None, None, None
 
 
+def _device_theta(flow: torch.Tensor, spatial_extent, cumulative: bool):
+    """theta (n, 2, 3) and copy mask (n,) for ``flow`` (b, 6) or, cumulative, (b, T, 6): fiery_warp_theta."""
+    _require_cuda(flow, "flow")
+    lib = _lib.load()
+    f = flow.detach().float().contiguous()
+    b = f.shape[0]
+    T = f.shape[1] if cumulative else 1
+    theta = torch.empty((b * T, 2, 3), dtype=torch.float32, device=f.device)
+    mask = torch.empty((b * T,), dtype=torch.uint8, device=f.device) if cumulative else None
+    with torch.cuda.device(f.device):
+        _lib.check(lib.fiery_warp_theta(b, T, 1 if cumulative else 0, f.data_ptr(), float(spatial_extent[0]),
+                                        float(spatial_extent[1]), theta.data_ptr(), mask.data_ptr() if cumulative else 0,
+                                        _stream_ptr(f.device)), "fiery_warp_theta")
+    return theta, mask
+
+
 def warp_features(x: torch.Tensor, flow, mode: str = "nearest", spatial_extent=None) -> torch.Tensor:
-    """Applies a z-rotation and xy translation to the feature map ``x (b, c, h, w)``; ``flow (b, 6)``; geometry.py:181-222."""
+    """Applies a z-rotation and xy translation to the feature map ``x (b, c, h, w)``; ``flow (b, 6)``; geometry.py:181-222.
+    Like the sampling kernels, theta is computed without autograd (the reference never trains through egomotion)."""
     if flow is None:
         return x
-    res = _WarpMaps.apply(x, _theta(flow, spatial_extent), None, _mode_flag(mode))
+    _require_cuda(x, "x")
+    theta, _ = _device_theta(flow, spatial_extent, cumulative=False)
+    res = _WarpMaps.apply(x, theta, None, _mode_flag(mode))
     return res if x.dtype == torch.float32 else res.to(x.dtype)
 
 
 def cumulative_warp_features(x: torch.Tensor, flow: torch.Tensor, mode: str = "nearest", spatial_extent=None) -> torch.Tensor:
     """Warps a sequence ``x (b, t, c, h, w)`` by accumulating incremental egomotion ``flow (b, t, 6)``: x[:, -1] stays, x[:, t]
-    is warped with flow[:, t] @ ... @ flow[:, -2]; geometry.py:225-253.  ONE kernel launch produces the whole result (past
-    frames sampled, present frame copied); the reference clones x, warps frame by frame and stacks."""
+    is warped with flow[:, t] @ ... @ flow[:, -2]; geometry.py:225-253.  Two kernel launches produce the whole result (pose
+    algebra; past frames sampled + present frame copied); the reference clones x, warps frame by frame and stacks."""
     b, T = x.shape[:2]
     if T == 1:
         return x
     _require_cuda(x, "x")
-    mats = pose_vec2mat(flow)                                                  # geometry.py:241
-    thetas = [None] * T
-    cum_flow = mats[:, -2]
-    for t in reversed(range(T - 1)):                                           # geometry.py:244-251
-        thetas[t] = _theta(mat2pose_vec(cum_flow), spatial_extent)
-        cum_flow = mats[:, t - 1] @ cum_flow
-    thetas[T - 1] = torch.zeros_like(thetas[0])                                # present frame: copied, theta unused
-    theta = torch.stack(thetas, 1).reshape(b * T, 2, 3)
-    copy_mask = torch.zeros((b, T), dtype=torch.uint8, device=x.device)
-    copy_mask[:, -1] = 1
+    theta, copy_mask = _device_theta(flow[:, :T], spatial_extent, cumulative=True)
     xm = x.reshape(b * T, *x.shape[2:])
-    res = _WarpMaps.apply(xm, theta, copy_mask.reshape(-1), _mode_flag(mode)).view(x.shape)
+    res = _WarpMaps.apply(xm, theta, copy_mask, _mode_flag(mode)).view(x.shape)
     return res if x.dtype == torch.float32 else res.to(x.dtype)

@@ -16,7 +16,7 @@
  *       exposes the integer voxel coordinates the reference computes at fiery.py:236-256 (for parity checks)
  *   fiery_compose_calibration
  *       exposes combined = R @ inverse(K), translation  (fiery.py:196,203)
- *   fiery_warp_features_forward / _backward
+ *   fiery_warp_features_forward / _backward, fiery_warp_theta
  *       replace affine_grid + grid_sample inside warp_features  fiery/utils/geometry.py:219-220 (called from
  *       cumulative_warp_features geometry.py:225-253, call site fiery.py:143)   [SURVEY.md section 8f, next-1]
  *
@@ -151,8 +151,7 @@ FIERY_API int fiery_voxels_summing_backward(int64_t n_rows, int32_t channels, co
  * site fiery/models/fiery.py:143-146): affine_grid + grid_sample (align_corners=False, zero padding; bilinear, or nearest
  * if `nearest` != 0) of n_maps feature maps (C, H, W) fp32 under the affine maps theta (n_maps, 2, 3).  Map m starts at
  * x + m * x_map_stride (elements); channel planes are dense (H*W).  copy_mask (n_maps bytes, may be NULL): maps with a
- * non-zero byte are copied unchanged -- the present frame of a sequence (geometry.py:243).  The pose algebra that yields
- * theta is tiny and stays with the caller (fiery_b200/warp.py mirrors geometry.py:197-219, 241-251).
+ * non-zero byte are copied unchanged -- the present frame of a sequence (geometry.py:243).
  * backward: grad_x[m] += adjoint of the sampling applied to grad_out[m]; grad_x must be zero-filled (or hold a running sum).
  */
 FIERY_API int fiery_warp_features_forward(int32_t n_maps, int32_t channels, int32_t height, int32_t width, const float* x,
@@ -161,6 +160,17 @@ FIERY_API int fiery_warp_features_forward(int32_t n_maps, int32_t channels, int3
 FIERY_API int fiery_warp_features_backward(int32_t n_maps, int32_t channels, int32_t height, int32_t width, const float* grad_out,
                                            int64_t grad_out_map_stride, const float* theta, const uint8_t* copy_mask,
                                            float* grad_x, int64_t grad_x_map_stride, int32_t nearest, void* stream);
+
+/*
+ * The pose algebra in front of the sampling: flow (6-DoF vectors tx,ty,tz,rx,ry,rz) -> theta (., 2, 3) for the calls above.
+ * cumulative != 0 replaces the loop of cumulative_warp_features (geometry.py:241-251: pose_vec2mat :145-160, the running
+ * product flow[t] @ ... @ flow[T-2], mat2pose_vec :82-107, then the theta of warp_features :197-219): flow is
+ * (n_sequences, T, 6), theta (n_sequences*T, 2, 3) and copy_mask (n_sequences*T bytes, required) are written; the last frame
+ * of every sequence is flagged "copy".  cumulative == 0 is the theta of a plain warp_features call: flow (n_sequences, 6),
+ * T ignored, copy_mask may be NULL.  spatial_extent_x/y as in geometry.py:205-206.
+ */
+FIERY_API int fiery_warp_theta(int32_t n_sequences, int32_t T, int32_t cumulative, const float* flow, float spatial_extent_x,
+                               float spatial_extent_y, float* theta, uint8_t* copy_mask, void* stream);
 
 #ifdef __cplusplus
 }

@@ -99,3 +99,24 @@ def test_gpu_full_size_properties():
     b = cumulative_warp_features(y, flow, mode="bilinear", spatial_extent=(50.0, 50.0))
     c = cumulative_warp_features(0.5 * x + y, flow, mode="bilinear", spatial_extent=(50.0, 50.0))
     assert float((0.5 * a + b - c).abs().max()) < 1e-4 * float(c.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T", [2, 3, 5])
+def test_gpu_pose_algebra_matches_oracle(T):
+    """fiery_warp_theta (pose_vec2mat, running product, mat2pose_vec, theta) against the oracle's torch-CPU restatement of
+    geometry.py:241-251 and :197-219; fp32, different summation order only."""
+    from fiery_b200.warp import _device_theta
+    dev = torch.device("cuda:0")
+    flow = torch.from_numpy(make_egomotion(4, T, seed=7 + T))
+    flow[:, :, 3:5] += 0.01 * torch.randn(4, T, 2, generator=torch.Generator().manual_seed(T))     # roll / pitch too
+    ext = (50.0, 25.0)
+    want = W.cumulative_warp_thetas(flow, ext)
+    theta, mask = _device_theta(flow.to(dev), ext, cumulative=True)
+    theta, mask = theta.cpu().view(4, T, 2, 3), mask.cpu().view(4, T)
+    assert mask[:, -1].eq(1).all() and mask[:, :-1].eq(0).all()
+    for t in range(T - 1):
+        np.testing.assert_allclose(theta[:, t].numpy(), want[t].numpy(), rtol=0, atol=2e-6)
+    plain, none = _device_theta(flow[:, 0].to(dev), ext, cumulative=False)
+    assert none is None
+    np.testing.assert_allclose(plain.cpu().numpy(), W.warp_theta(flow[:, 0], ext).numpy(), rtol=0, atol=1e-6)
