@@ -43,7 +43,7 @@ __device__ __forceinline__ void flush_pair_if(char* dst, unsigned long long lo, 
 }
 
 template <int DBLKS>
-__global__ void __launch_bounds__(64 * DBLKS, 2)
+__global__ void __launch_bounds__(64 * DBLKS, 3)
 lift_forward_kernel(const __grid_constant__ HeadMaps head_maps, const LiftParams P) {
     using TL = TileLayout<DBLKS>;
     constexpr int DPAD = TL::DPAD;
@@ -298,6 +298,9 @@ static int launch_forward_t(const HeadMaps& map, const LiftParams& P, cudaStream
     if (!configured) {
         FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_kernel<DBLKS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               227 * 1024));
+        // three tiles per SM (3 x 74 KB for the reference shape): ask for the full shared-memory carve-out
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_kernel<DBLKS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     FIERY_REQUIRE(L.total <= 227 * 1024, "tile needs %d bytes of shared memory", L.total);

@@ -59,7 +59,13 @@ struct TileLayout {
         off_u = o;      o += WT * 4;
         off_d = o;      o += DPAD * 4;
         off_v = o;      o += ((hh + 3) & ~3) * 4;
-        off_red = o;    o += 2 * (DPAD / 16) * PX * 4;   // softmax partial max / sum per (depth group of 16, pixel)
+        // softmax partial max / sum per (depth group of 16, pixel); dead after transform_tile, so the run-end tables, which
+        // are written after the barrier that follows stage_pillars, share the bytes
+        const int red_bytes = 2 * (DPAD / 16) * PX * 4;
+        const int chg_bytes = (PX * DBLKS + 15) & ~15;
+        const int ev_bytes = NWARPS * 32 * 4;    // forward: per (warp, row) run-end events, see stage_events
+        off_red = o;    off_chg = o;    off_ev = o + chg_bytes;
+        o += (red_bytes > chg_bytes + ev_bytes ? red_bytes : chg_bytes + ev_bytes);
         o = (o + 127) & ~127;
         const int prob_raw = DPAD * PX * 4, prob_t = PX * PS * 4;
         off_prob = o;   o += (prob_raw > prob_t ? prob_raw : prob_t);
@@ -67,8 +73,6 @@ struct TileLayout {
         off_ctx = o;    o += C * PX * 4;
         o = (o + 127) & ~127;
         off_pillar = o; o += PX * DPAD * 4;
-        off_chg = o;    o += ((PX * DBLKS + 15) & ~15);
-        off_ev = o;     o += NWARPS * 32 * 4;    // forward: per (warp, row) run-end events, see stage_events
         total = o;
     }
 };
