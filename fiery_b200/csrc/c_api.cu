@@ -76,6 +76,47 @@ int encode_head_maps(HeadMaps* maps, const void* head, int dtype, const LiftPara
     return encode_view(&maps->ctx, head, n_images, P.head_channels, P.use_depth ? P.D : 0, P.C, P.hh, P.ww);
 }
 
+// Tensor maps of the column-packed forward kernel (lift_fwd_cols.cu): the tile arrives as prob[row][depth][col4] and
+// ctx[row][k][cl][col4] with channel = CPL*cl + k -- the dimension order of the maps is the shared-memory order, the strides do
+// the permutation.
+struct HeadMapsCols {
+    CUtensorMap depth;
+    CUtensorMap ctx;
+};
+
+int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams& P, int channels_per_lane) {
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const size_t es = 4;
+    const cuuint64_t ww = P.ww, hh = P.hh, n_images = static_cast<cuuint64_t>(P.n_frames) * P.n_cameras;
+    const cuuint64_t plane = ww * hh * es, image = plane * P.head_channels;
+    FIERY_REQUIRE((reinterpret_cast<uintptr_t>(head) & 15) == 0 && (plane * (P.use_depth ? P.D : 0)) % 16 == 0,
+                  "head tensor (or its context slice) is not 16-byte aligned");
+    const int cpl = channels_per_lane;
+    FIERY_REQUIRE(cpl >= 1 && P.C % cpl == 0 && P.C / cpl <= 256 && hh <= 256, "column kernel: unsupported head shape");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (P.use_depth) {
+        cuuint64_t dims[4] = {ww, static_cast<cuuint64_t>(P.D), hh, n_images};
+        cuuint64_t strides[3] = {plane, ww * es, image};
+        cuuint32_t box[4] = {WT, 48, static_cast<cuuint32_t>(hh), 1};
+        CUresult r = fn(&maps->depth, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(head), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled (depth, 4-D) failed with CUresult %d", (int)r);
+    } else {
+        memset(&maps->depth, 0, sizeof(CUtensorMap));
+    }
+    const char* ctx_base = static_cast<const char*>(head) + plane * (P.use_depth ? P.D : 0);
+    cuuint64_t dims[5] = {ww, static_cast<cuuint64_t>(P.C / cpl), static_cast<cuuint64_t>(cpl), hh, n_images};
+    cuuint64_t strides[4] = {cpl * plane, plane, ww * es, image};
+    cuuint32_t box[5] = {WT, static_cast<cuuint32_t>(P.C / cpl), static_cast<cuuint32_t>(cpl), static_cast<cuuint32_t>(hh), 1};
+    CUresult r = fn(&maps->ctx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<char*>(ctx_base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled (context, 5-D) failed with CUresult %d", (int)r);
+    return FIERY_OK;
+}
+
 // launchers defined next to their kernels
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch, cudaStream_t);
 int lift_chunk_frames(int n_frames, long long pillars, int channels);

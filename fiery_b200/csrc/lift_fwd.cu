@@ -12,6 +12,9 @@
 // (a precomputed change bit, rare) does it flush its partial sum with one 16-byte vector reduction
 // (red.global.add.v4.f32) into a channel-last BEV accumulator.  Sixteen lanes of a half-warp cover the 64 channels of
 // a pillar, so each flush is two full 128-byte lines.  ~17k column segments per frame reach L2 instead of 453k points.
+#include <cstdlib>
+#include <cstring>
+
 #include "lift_tile.cuh"
 
 namespace fiery {
@@ -321,21 +324,36 @@ int lift_chunk_frames(int n_frames, long long pillars, int channels) {
     return static_cast<int>(c < 1 ? 1 : c);
 }
 
+int launch_forward_cols(const LiftParams& P, const void* head, int variant, cudaStream_t stream);
+
+// FIERY_LIFT_FORWARD=rows selects the row-major tile kernel of this file (kept as the A/B partner of lift_fwd_cols.cu)
+static int use_cols_kernel() {        // 0: rows kernel, else the column kernel variant (see launch_forward_cols)
+    static const int cols = [] {
+        const char* e = getenv("FIERY_LIFT_FORWARD");
+        if (e && strcmp(e, "rows") == 0) return 0;
+        if (e && strcmp(e, "cols3") == 0) return 43;
+        if (e && strcmp(e, "cols2") == 0) return 42;
+        return 22;
+    }();
+    return cols;
+}
+
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch,
                         cudaStream_t stream) {
     FIERY_REQUIRE(head_dtype == FIERY_DTYPE_F32, "head dtype %d not supported by this build (fp32 only)", head_dtype);
     FIERY_REQUIRE(P.C == 64, "channels=%d not supported by this build (C must be 64)", P.C);
     FIERY_REQUIRE(P.D >= 1 && P.D <= 48, "depth_bins=%d not supported by this build (1..48)", P.D);
     FIERY_REQUIRE(P.ww % 4 == 0, "feat_w=%d must be a multiple of 4 (TMA row pitch must be 16-byte aligned)", P.ww);
+    const int cols = use_cols_kernel();
     HeadMaps map;
-    int rc = encode_head_maps(&map, head, head_dtype, P);
+    int rc = cols ? FIERY_OK : encode_head_maps(&map, head, head_dtype, P);
     if (rc != FIERY_OK) return rc;
     LiftParams Q = P;
     if (P.bev_layout == FIERY_BEV_NHWC) {          // the caller's zero-filled channel-last tensor is the accumulator
         Q.accum = bev_out;
         Q.touched = nullptr;
         Q.frame0 = 0;
-        return launch_forward_t<6>(map, Q, stream);
+        return cols ? launch_forward_cols(Q, head, cols, stream) : launch_forward_t<6>(map, Q, stream);
     }
     // NCHW: lift into the channel-last accumulator, then the layout pass; chunked only to bound the scratch footprint
     const int chunk = lift_chunk_frames(P.n_frames, P.pillars, P.C);
@@ -345,7 +363,7 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     for (int f0 = 0; f0 < P.n_frames; f0 += chunk) {
         Q.frame0 = f0;
         Q.n_frames = (P.n_frames - f0 < chunk) ? P.n_frames - f0 : chunk;
-        rc = launch_forward_t<6>(map, Q, stream);
+        rc = cols ? launch_forward_cols(Q, head, cols, stream) : launch_forward_t<6>(map, Q, stream);
         if (rc != FIERY_OK) return rc;
         if (P.pillars % 4 == 0) {
             const int bpf4 = static_cast<int>((P.pillars / 4 + FIN_THREADS - 1) / FIN_THREADS);

@@ -1,0 +1,364 @@
+// Forward lift, column-packed tile kernel.
+//
+// Same job and same arithmetic as lift_forward_kernel (lift_fwd.cu): get_geometry (fiery.py:193-208), depth softmax x
+// context outer product (encoder.py:98-100) and the voxel pooling of projection_to_birds_eye_view (fiery.py:221-273) for one
+// tile = one camera image x 4 feature columns x all rows x all depths x all channels, accumulated with vector reductions into
+// the channel-last accumulator.  What differs is the shared-memory layout, chosen so that NOTHING is transposed:
+//
+//   * the two TMA loads deliver the tile as  prob[row][depth][col4]  and  ctx[row][k][cl][col4]  (channel CPL*cl + k; the
+//     channel split is a 5-D tensor map, so the permutation is done by the copy engine).  One 16-byte shared load is then
+//     "4 adjacent columns of one (row, depth)" or "... of one (row, channel)";
+//   * a thread owns 2 depths x 4 columns x CPL channels, held as packed pairs of ADJACENT COLUMNS, so the outer product is
+//     4*CPL FFMA2 per row whose operands are exactly the register pairs the loads return;
+//   * the softmax runs in place on prob (lane = (depth mod 8, column): conflict free, reductions by shuffle) while one lane
+//     composes the camera matrix;
+//   * run ends are detected warp-uniformly (one 16-bit load + one warp reduction per row, fetched a row ahead).
+#include "lift_tile.cuh"
+
+namespace fiery {
+
+constexpr int COLS_DPAD = 48;                 // depth slots (D <= 48)
+constexpr int COLS_NU = COLS_DPAD / 2;        // units of 2 depths: one per half-warp
+constexpr int COLS_NT = COLS_NU * 16;         // 384 threads
+constexpr int COLS_NW = COLS_NT / 32;
+
+struct HeadMapsCols {
+    CUtensorMap depth;    // 4-D (w, d, h, image), box (4, 48, h, 1)
+    CUtensorMap ctx;      // 5-D (w, cl, k, h, image), box (4, 64/CPL, CPL, h, 1): channel = CPL*cl + k
+};
+
+struct ColsLayout {
+    int hh, C;
+    int off_bar, off_cam, off_u, off_v, off_d, off_ev, off_prob, off_ctx, off_pillar, total;
+    __host__ __device__ ColsLayout(int hh_, int C_) : hh(hh_), C(C_) {
+        int o = 0;
+        off_bar = o;    o += 16;
+        off_cam = o;    o += 12 * 4;
+        off_u = o;      o += WT * 4;
+        off_v = o;      o += 32 * 4;
+        off_d = o;      o += COLS_DPAD * 4;
+        o = (o + 15) & ~15;
+        off_ev = o;     o += COLS_NU * 32 * 2;         // run-end events: [unit][row] 16 bits, see stage_events_cols
+        o = (o + 127) & ~127;
+        off_prob = o;   o += hh * COLS_DPAD * WT * 4;
+        o = (o + 127) & ~127;
+        off_ctx = o;    o += hh * C * WT * 4;
+        o = (o + 127) & ~127;
+        off_pillar = o; o += hh * COLS_NU * 8 * 4;     // [row][unit][j = dd*4 + col]
+        total = o;
+    }
+};
+
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+// packed fp32x2 FMA (SASS FFMA2) on two adjacent columns: acc.lo += a.lo * b.lo, acc.hi += a.hi * b.hi
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
+template <int HALF>
+__device__ __forceinline__ float half_of(unsigned long long v) {
+    return __uint_as_float(HALF ? static_cast<unsigned>(v >> 32) : static_cast<unsigned>(v));
+}
+
+// zero one half of a packed pair where keep == 0 (keep is 0 or ~0): one logic op on one register of the pair, in place
+template <int HALF>
+__device__ __forceinline__ void clear_half(unsigned long long& v, unsigned keep) {
+    v &= HALF ? ((static_cast<unsigned long long>(keep) << 32) | 0xffffffffull) : (0xffffffff00000000ull | keep);
+}
+
+// pair p = unit * 8 + j, j = dd * 4 + col: depth 2 * unit + dd, column col of the tile.  pillar[row][unit][j]
+template <bool POW2, int NT>
+__device__ __forceinline__ void stage_pillars_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem, int w0) {
+    constexpr int NPAIR = COLS_NU * 8;
+    constexpr int NRS = NT / NPAIR;                          // row ranges per pair, so that every thread has one work item
+    const float* s_cam = reinterpret_cast<const float*>(smem + L.off_cam);
+    const float* s_u = reinterpret_cast<const float*>(smem + L.off_u);
+    const float* s_v = reinterpret_cast<const float*>(smem + L.off_v);
+    const float* s_d = reinterpret_cast<const float*>(smem + L.off_d);
+    int* s_pillar = reinterpret_cast<int*>(smem + L.off_pillar);
+    CameraTransform T;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) T.m[i] = s_cam[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) T.t[i] = s_cam[9 + i];
+    const float offx = P.grid.off[0], offy = P.grid.off[1], offz = P.grid.off[2];
+    const float kx = POW2 ? P.grid.inv_res[0] : P.grid.res[0], ky = POW2 ? P.grid.inv_res[1] : P.grid.res[1];
+    const float Xf = static_cast<float>(P.grid.X), Yf = static_cast<float>(P.grid.Y);
+    const float z_lo = P.grid.z_lo, z_hi = P.grid.z_hi;
+    const int Y = P.grid.Y;
+    const int pair = threadIdx.x % NPAIR, rs = threadIdx.x / NPAIR;
+    const int unit = pair >> 3, j = pair & 7;
+    const int d = unit * 2 + (j >> 2), col = j & 3;
+    const int h_lo = (L.hh * rs) / NRS, h_hi = (L.hh * (rs + 1)) / NRS;
+    int* out = s_pillar + (h_lo * COLS_NU + unit) * 8 + j;
+    if (d >= P.D || w0 + col >= P.ww) {
+        for (int h = h_lo; h < h_hi; ++h, out += COLS_NU * 8) *out = -1;
+        return;
+    }
+    const float depth = s_d[d];
+    const ColumnTerms ct = column_terms(T, s_u[col], depth);
+#pragma unroll 2
+    for (int h = h_lo; h < h_hi; ++h, out += COLS_NU * 8) {
+        float p[3];
+        ego_point(T, ct, s_v[h], depth, p);                               // fiery.py:199-205
+        const float ax = __fsub_rn(p[0], offx), ay = __fsub_rn(p[1], offy), az = __fsub_rn(p[2], offz);
+        const float sx = POW2 ? __fmul_rn(ax, kx) : __fdiv_rn(ax, kx);    // fiery.py:236 (x scale exact when res is 2^k)
+        const float sy = POW2 ? __fmul_rn(ay, ky) : __fdiv_rn(ay, ky);
+        const int rank = static_cast<int>(sx) * Y + static_cast<int>(sy); // truncation, fiery.py:237,252-256
+        *out = select_pillar(sx, sy, az, Xf, Yf, z_lo, z_hi, rank);       // mask, fiery.py:240-247
+    }
+}
+
+// Run-end events per (unit, row) + marks for the layout pass.  ev[unit][row]: bit j (j = dd*4 + col) set <=> pair j changes
+// pillar between row-1 and row; bit 8+j: ... and the run that ends sits on a valid pillar (it must be flushed, the others are
+// only cleared).  Every pillar that starts a run is marked in the `touched` map of the layout pass here, so that the pooling
+// loop itself only issues reductions.
+template <int NT>
+__device__ __forceinline__ void stage_events_cols(const ColsLayout& L, unsigned char* smem, unsigned char* touched) {
+    const int* s_pillar = reinterpret_cast<const int*>(smem + L.off_pillar);
+    unsigned short* s_ev = reinterpret_cast<unsigned short*>(smem + L.off_ev);
+    for (int item = threadIdx.x; item < COLS_NU * L.hh; item += NT) {
+        const int unit = item % COLS_NU, row = item / COLS_NU;      // consecutive lanes: consecutive 32-byte rows of the table
+        unsigned chg = 0, fl = 0;
+        const int4* cur = reinterpret_cast<const int4*>(s_pillar + item * 8);
+        const int4 c0 = cur[0], c1 = cur[1];
+        const int c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        int p[8];
+        if (row > 0) {
+            const int4* prv = cur - 2 * COLS_NU;
+            const int4 p0 = prv[0], p1 = prv[1];
+            p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool change = row > 0 && c[j] != p[j];
+            if (change) {
+                chg |= 1u << j;
+                if (p[j] >= 0) fl |= 1u << j;
+            }
+            if (touched && (row == 0 || change) && c[j] >= 0) touched[c[j]] = 0x0f;   // one bit per channel quarter
+        }
+        s_ev[unit * 32 + row] = static_cast<unsigned short>(chg | (fl << 8));
+    }
+}
+
+// softmax over depth (encoder.py:99) in place on prob[row][d][col]; lane = (d mod 8, col)
+template <int NT>
+__device__ __forceinline__ void softmax_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem) {
+    constexpr float L2E = 1.4426950408889634f;
+    float* s_prob = reinterpret_cast<float*>(smem + L.off_prob);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c8 = lane >> 2, col = lane & 3;
+    for (int row = warp; row < L.hh; row += NT / 32) {
+        float* base = s_prob + (row * COLS_DPAD + c8) * WT + col;
+        float x[COLS_DPAD / 8];
+        if (P.use_depth) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < COLS_DPAD / 8; ++k) {
+                x[k] = (c8 + 8 * k < P.D) ? base[k * 8 * WT] : -INFINITY;
+                m = fmaxf(m, x[k]);
+            }
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+            const float m2 = m * L2E;
+            float sum = 0.f;
+#pragma unroll
+            for (int k = 0; k < COLS_DPAD / 8; ++k) {
+                x[k] = exp2f(fmaf(x[k], L2E, -m2));         // exp(x - max); padding (-inf) gives 0
+                sum += x[k];
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+            const float inv = __fdiv_rn(1.0f, sum);
+#pragma unroll
+            for (int k = 0; k < COLS_DPAD / 8; ++k) base[k * 8 * WT] = x[k] * inv;
+        } else {
+#pragma unroll
+            for (int k = 0; k < COLS_DPAD / 8; ++k) base[k * 8 * WT] = (c8 + 8 * k < P.D) ? 1.0f : 0.f;   // encoder.py:102
+        }
+    }
+}
+
+// predicated vector reduction of CPL adjacent channels
+template <int CPL>
+__device__ __forceinline__ void red_channels_if(char* dst, const float (&v)[CPL], unsigned bit) {
+    if (CPL == 4)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+                     :: "l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[CPL > 2 ? 2 : 0]), "f"(v[CPL > 3 ? 3 : 0]), "r"(bit) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p red.global.add.v2.f32 [%0], {%1, %2};\n\t}"
+                     :: "l"(dst), "f"(v[0]), "f"(v[1]), "r"(bit) : "memory");
+}
+
+// One (depth, column) slot of the run-end handling.  `mw` is warp-uniform, so the test is a plain branch; the lanes that own
+// the ending run reduce their channels into the accumulator and restart.  The "+ 0.0f" copies are real instructions on
+// purpose: they gather the values into the consecutive registers the vector reduction needs HERE, instead of letting the
+// register allocator keep the accumulators in that order and un-shuffle them around every FFMA2.
+template <int CPL, int DD, int COL>
+__device__ __forceinline__ void flush_slot(unsigned long long (&acc)[CPL][2][2], unsigned mw, unsigned own, const int* plp, char* out) {
+    constexpr int j = DD * 4 + COL;
+    if (mw & (1u << j)) {
+        const unsigned pl = static_cast<unsigned>(plp[j]);
+        float v[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) v[k] = __fadd_rn(half_of<COL & 1>(acc[k][DD][COL >> 1]), 0.0f);
+        red_channels_if<CPL>(out + static_cast<size_t>(pl) * (64 * 4), v, own & (0x100u << j));
+        const unsigned keep = ((own >> j) & 1u) - 1u;          // 0 where my run ends, ~0 otherwise
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) clear_half<COL & 1>(acc[k][DD][COL >> 1], keep);
+    }
+}
+
+// CPL channels per lane: 4 -> a unit is a half-warp, 384 threads; 2 -> a unit is a warp, 768 threads
+template <int CPL, int MINB>
+__global__ void __launch_bounds__(COLS_NU * (64 / CPL), MINB)
+lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const LiftParams P) {
+    constexpr int LPU = 64 / CPL;                     // lanes per unit
+    constexpr int NT = COLS_NU * LPU;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const ColsLayout L(P.hh, P.C);
+    const int wtile = blockIdx.x % P.n_wtiles;
+    const int img_local = blockIdx.x / P.n_wtiles;    // (frame, camera) within this launch's chunk of frames
+    const int img = P.frame0 * P.n_cameras + img_local;
+    const int frame = img_local / P.n_cameras;        // chunk-local: indexes the accumulator
+    const int w0 = wtile * WT;
+    const int tid = threadIdx.x;
+    const int hh = L.hh;
+
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    if (tid == 0) {
+        tma_prefetch_desc(&head_maps.depth);
+        tma_prefetch_desc(&head_maps.ctx);
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        const uint32_t prob_bytes = P.use_depth ? static_cast<uint32_t>(hh * COLS_DPAD * WT * 4) : 0u;
+        mbar_arrive_expect_tx(bar, prob_bytes + static_cast<uint32_t>(hh * L.C * WT * 4));
+        if (P.use_depth) tma_load_4d(smem + L.off_prob, &head_maps.depth, bar, w0, 0, 0, img);
+        tma_load_5d(smem + L.off_ctx, &head_maps.ctx, bar, w0, 0, 0, 0, img);
+    }
+    {   // constants of the tile
+        float* s_u = reinterpret_cast<float*>(smem + L.off_u);
+        float* s_v = reinterpret_cast<float*>(smem + L.off_v);
+        float* s_d = reinterpret_cast<float*>(smem + L.off_d);
+        if (tid < WT) s_u[tid] = (w0 + tid < P.ww) ? P.fu[w0 + tid] : 0.f;
+        if (tid >= 32 && tid < 64) s_v[tid - 32] = P.fv[min(tid - 32, hh - 1)];
+        if (tid >= 64 && tid < 64 + COLS_DPAD) s_d[tid - 64] = (tid - 64 < P.D) ? P.fd[tid - 64] : 0.f;
+    }
+    __syncthreads();                                  // mbarrier init visible before anyone polls it
+    // one lane composes R @ K^-1 (fiery.py:203) while the TMA is in flight and the others run the softmax
+    if (tid == NT - 1) {
+        CameraTransform T;
+        load_camera(P.calib_mode, P.calib_a, P.calib_b, img, T);
+        float* s_cam = reinterpret_cast<float*>(smem + L.off_cam);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) s_cam[i] = T.m[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) s_cam[9 + i] = T.t[i];
+    }
+    mbar_wait(bar, 0);                                // head tile has landed
+    softmax_cols<NT>(P, L, smem);
+    __syncthreads();
+    if (P.grid.pow2[0] && P.grid.pow2[1]) stage_pillars_cols<true, NT>(P, L, smem, w0);
+    else stage_pillars_cols<false, NT>(P, L, smem, w0);
+    __syncthreads();
+    stage_events_cols<NT>(L, smem, P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr);
+    __syncthreads();
+
+    // ---- pooling: thread = (unit of 2 depths, 4 columns, channels CPL*cl .. CPL*cl + CPL-1) ---------------------------
+    const int unit = tid / LPU;
+    const int cl = tid % LPU;
+    const float* pp = reinterpret_cast<const float*>(smem + L.off_prob) + unit * 2 * WT;
+    const float* cp = reinterpret_cast<const float*>(smem + L.off_ctx) + cl * WT;
+    const int* plp = reinterpret_cast<const int*>(smem + L.off_pillar) + unit * 8 - COLS_NU * 8;       // row h-1
+    char* out = reinterpret_cast<char*>(P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cl * CPL);
+    const unsigned short* evp = reinterpret_cast<const unsigned short*>(smem + L.off_ev) + unit * 32;
+
+    unsigned long long acc[CPL][2][2];                // [channel k][depth dd][column pair]
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) acc[k][0][0] = acc[k][0][1] = acc[k][1][0] = acc[k][1][1] = 0ull;
+
+    // own: bits 0-7 my runs that end at this row, bits 8-15 ... and must be flushed.  mw: slots that end a run anywhere in
+    // the warp -- a warp reduction, so every run-end branch is warp-uniform (half-warps that own different depths would
+    // otherwise diverge on every event).  Both are fetched one row ahead: the chain load -> reduce -> branch is long.
+    unsigned own = 0, mw = 0;                         // row 0 starts every run
+#pragma unroll 2
+    for (int h = 0; h < hh; ++h, pp += COLS_DPAD * WT, cp += 64 * WT, plp += COLS_NU * 8) {
+        const unsigned own_next = evp[h + 1 < hh ? h + 1 : 0];       // row 0 holds no event
+        if (mw) {
+            if (mw & 0x0fu) {
+                flush_slot<CPL, 0, 0>(acc, mw, own, plp, out); flush_slot<CPL, 0, 1>(acc, mw, own, plp, out);
+                flush_slot<CPL, 0, 2>(acc, mw, own, plp, out); flush_slot<CPL, 0, 3>(acc, mw, own, plp, out);
+            }
+            if (mw & 0xf0u) {
+                flush_slot<CPL, 1, 0>(acc, mw, own, plp, out); flush_slot<CPL, 1, 1>(acc, mw, own, plp, out);
+                flush_slot<CPL, 1, 2>(acc, mw, own, plp, out); flush_slot<CPL, 1, 3>(acc, mw, own, plp, out);
+            }
+        }
+        const ulonglong2 d0 = *reinterpret_cast<const ulonglong2*>(pp);           // depth 2u:   columns (0,1) (2,3)
+        const ulonglong2 d1 = *reinterpret_cast<const ulonglong2*>(pp + WT);      // depth 2u+1
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(cp + k * LPU * WT);   // channel CPL*cl + k
+            // depth x context outer product (encoder.py:100), summed along the column
+            ffma2(acc[k][0][0], d0.x, c.x); ffma2(acc[k][0][1], d0.y, c.y);
+            ffma2(acc[k][1][0], d1.x, c.x); ffma2(acc[k][1][1], d1.y, c.y);
+        }
+        own = own_next;
+        mw = __reduce_or_sync(0xffffffffu, own & 0xffu);
+    }
+    // the runs that reach the last row (plp now points at it)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int pl = plp[j];
+        float v[CPL];
+#pragma unroll
+        for (int k = 0; k < CPL; ++k) {
+            const unsigned long long a = acc[k][j >> 2][(j & 3) >> 1];
+            v[k] = (j & 1) ? half_of<1>(a) : half_of<0>(a);
+        }
+        red_channels_if<CPL>(out + static_cast<size_t>(static_cast<unsigned>(pl)) * (64 * 4), v, pl >= 0 ? 1u : 0u);
+    }
+}
+
+int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams& P, int channels_per_lane);
+
+template <int CPL, int MINB>
+static int launch_forward_cols_t(const HeadMapsCols& maps, const LiftParams& P, cudaStream_t stream) {
+    const ColsLayout L(P.hh, P.C);
+    static bool configured = false;
+    if (!configured) {
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        // ask for the full shared-memory carve-out (3 x 74 KB per SM for the reference shape)
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              cudaSharedmemCarveoutMaxShared));
+        configured = true;
+    }
+    FIERY_REQUIRE(L.total <= 227 * 1024, "tile needs %d bytes of shared memory", L.total);
+    const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
+    lift_forward_cols_kernel<CPL, MINB><<<static_cast<unsigned>(n_tiles), COLS_NU * (64 / CPL), L.total, stream>>>(maps, P);
+    FIERY_CUDA_CHECK(cudaGetLastError());
+    return FIERY_OK;
+}
+
+// variant: 42 = 4 channels per lane, 2 tiles per SM; 43 = 4 channels, 3 tiles; 22 = 2 channels per lane (768 threads), 2 tiles
+int launch_forward_cols(const LiftParams& P, const void* head, int variant, cudaStream_t stream) {
+    FIERY_REQUIRE(P.hh <= 32, "feat_h=%d not supported by this build (<= 32)", P.hh);
+    FIERY_REQUIRE(P.C == 64 && P.D <= COLS_DPAD, "column kernel: C=%d D=%d not supported", P.C, P.D);
+    HeadMapsCols maps;
+    const int rc = encode_head_maps_cols(&maps, head, P, variant == 22 ? 2 : 4);
+    if (rc != FIERY_OK) return rc;
+    if (variant == 22) return launch_forward_cols_t<2, 2>(maps, P, stream);
+    if (variant == 43) return launch_forward_cols_t<4, 3>(maps, P, stream);
+    return launch_forward_cols_t<4, 2>(maps, P, stream);
+}
+
+}  // namespace fiery
