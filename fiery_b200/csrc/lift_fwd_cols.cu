@@ -21,6 +21,7 @@ constexpr int COLS_DPAD = 48;                 // depth slots (D <= 48)
 constexpr int COLS_NU = COLS_DPAD / 2;        // units of 2 depths: one per half-warp
 constexpr int COLS_NT = COLS_NU * 16;         // 384 threads
 constexpr int COLS_NW = COLS_NT / 32;
+constexpr int COLS_EVS = 33;                  // event words per unit: rows 0..31 + one that stays 0
 
 struct HeadMapsCols {
     CUtensorMap depth;    // 4-D (w, d, h, image), box (4, 48, h, 1)
@@ -38,7 +39,7 @@ struct ColsLayout {
         off_v = o;      o += 32 * 4;
         off_d = o;      o += COLS_DPAD * 4;
         o = (o + 15) & ~15;
-        off_ev = o;     o += COLS_NU * 32 * 2;         // run-end events: [unit][row] 16 bits, see stage_events_cols
+        off_ev = o;     o += COLS_NU * COLS_EVS * 4;   // run-end events: [unit][row], see stage_geometry_cols
         o = (o + 127) & ~127;
         off_prob = o;   o += hh * COLS_DPAD * WT * 4;
         o = (o + 127) & ~127;
@@ -72,16 +73,25 @@ __device__ __forceinline__ void clear_half(unsigned long long& v, unsigned keep)
     v &= HALF ? ((static_cast<unsigned long long>(keep) << 32) | 0xffffffffull) : (0xffffffff00000000ull | keep);
 }
 
-// pair p = unit * 8 + j, j = dd * 4 + col: depth 2 * unit + dd, column col of the tile.  pillar[row][unit][j]
+// Geometry of the tile: the pillar (rank, fiery.py:236-256; -1 = masked) of every point, evaluated with the reference
+// arithmetic, reduced on the fly to what the pooling loop consumes:
+//   ev[unit][row]      bit j (j = dd*4 + col: depth 2*unit + dd, column col) set <=> pair j changes pillar between row-1 and
+//                      row; bit 8+j: ... and the run that ends sits on a valid pillar (it must be flushed, the others are
+//                      only cleared)
+//   pillar[row][unit][j]  written only where it is read: the last row of every run
+//   touched[pillar]    the layout pass's map of pillars that receive something, marked at every run start
+// thread = (pair, row range); the NRS ranges of a pair sit in adjacent lanes and hand their last pillar to the next range.
 template <bool POW2, int NT>
-__device__ __forceinline__ void stage_pillars_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem, int w0) {
+__device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem, int w0,
+                                                    unsigned char* touched) {
     constexpr int NPAIR = COLS_NU * 8;
-    constexpr int NRS = NT / NPAIR;                          // row ranges per pair, so that every thread has one work item
+    constexpr int NRS = NT / NPAIR;
     const float* s_cam = reinterpret_cast<const float*>(smem + L.off_cam);
     const float* s_u = reinterpret_cast<const float*>(smem + L.off_u);
     const float* s_v = reinterpret_cast<const float*>(smem + L.off_v);
     const float* s_d = reinterpret_cast<const float*>(smem + L.off_d);
     int* s_pillar = reinterpret_cast<int*>(smem + L.off_pillar);
+    unsigned* s_ev = reinterpret_cast<unsigned*>(smem + L.off_ev);
     CameraTransform T;
 #pragma unroll
     for (int i = 0; i < 9; ++i) T.m[i] = s_cam[i];
@@ -92,59 +102,49 @@ __device__ __forceinline__ void stage_pillars_cols(const LiftParams& P, const Co
     const float Xf = static_cast<float>(P.grid.X), Yf = static_cast<float>(P.grid.Y);
     const float z_lo = P.grid.z_lo, z_hi = P.grid.z_hi;
     const int Y = P.grid.Y;
-    const int pair = threadIdx.x % NPAIR, rs = threadIdx.x / NPAIR;
+    const int hh = L.hh;
+    const int pair = threadIdx.x / NRS, rs = threadIdx.x % NRS;
     const int unit = pair >> 3, j = pair & 7;
     const int d = unit * 2 + (j >> 2), col = j & 3;
-    const int h_lo = (L.hh * rs) / NRS, h_hi = (L.hh * (rs + 1)) / NRS;
-    int* out = s_pillar + (h_lo * COLS_NU + unit) * 8 + j;
-    if (d >= P.D || w0 + col >= P.ww) {
-        for (int h = h_lo; h < h_hi; ++h, out += COLS_NU * 8) *out = -1;
-        return;
-    }
-    const float depth = s_d[d];
-    const ColumnTerms ct = column_terms(T, s_u[col], depth);
-#pragma unroll 2
-    for (int h = h_lo; h < h_hi; ++h, out += COLS_NU * 8) {
-        float p[3];
-        ego_point(T, ct, s_v[h], depth, p);                               // fiery.py:199-205
-        const float ax = __fsub_rn(p[0], offx), ay = __fsub_rn(p[1], offy), az = __fsub_rn(p[2], offz);
-        const float sx = POW2 ? __fmul_rn(ax, kx) : __fdiv_rn(ax, kx);    // fiery.py:236 (x scale exact when res is 2^k)
-        const float sy = POW2 ? __fmul_rn(ay, ky) : __fdiv_rn(ay, ky);
-        const int rank = static_cast<int>(sx) * Y + static_cast<int>(sy); // truncation, fiery.py:237,252-256
-        *out = select_pillar(sx, sy, az, Xf, Yf, z_lo, z_hi, rank);       // mask, fiery.py:240-247
-    }
-}
+    const bool split = hh >= 2 * NRS;                       // short columns: one lane of the pair walks all rows
+    const int h_lo = split ? (hh * rs) / NRS : 0;
+    const int h_hi = split ? (hh * (rs + 1)) / NRS : (rs == 0 ? hh : 0);
+    const bool dead = d >= P.D || w0 + col >= P.ww;
 
-// Run-end events per (unit, row) + marks for the layout pass.  ev[unit][row]: bit j (j = dd*4 + col) set <=> pair j changes
-// pillar between row-1 and row; bit 8+j: ... and the run that ends sits on a valid pillar (it must be flushed, the others are
-// only cleared).  Every pillar that starts a run is marked in the `touched` map of the layout pass here, so that the pooling
-// loop itself only issues reductions.
-template <int NT>
-__device__ __forceinline__ void stage_events_cols(const ColsLayout& L, unsigned char* smem, unsigned char* touched) {
-    const int* s_pillar = reinterpret_cast<const int*>(smem + L.off_pillar);
-    unsigned short* s_ev = reinterpret_cast<unsigned short*>(smem + L.off_ev);
-    for (int item = threadIdx.x; item < COLS_NU * L.hh; item += NT) {
-        const int unit = item % COLS_NU, row = item / COLS_NU;      // consecutive lanes: consecutive 32-byte rows of the table
-        unsigned chg = 0, fl = 0;
-        const int4* cur = reinterpret_cast<const int4*>(s_pillar + item * 8);
-        const int4 c0 = cur[0], c1 = cur[1];
-        const int c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-        int p[8];
-        if (row > 0) {
-            const int4* prv = cur - 2 * COLS_NU;
-            const int4 p0 = prv[0], p1 = prv[1];
-            p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
+    unsigned* ev = s_ev + unit * COLS_EVS;
+    int* tab = s_pillar + unit * 8 + j;
+    auto run_ends = [&](int h, int before, int now) {        // rows h-1 | h lie in different pillars
+        atomicOr(ev + h, (1u << j) | (before >= 0 ? (0x100u << j) : 0u));
+        if (before >= 0) tab[(h - 1) * (COLS_NU * 8)] = before;
+        if (touched && now >= 0) touched[now] = 0x0f;       // one bit per channel quarter of the layout pass
+    };
+
+    int first = -1, prev = -1;
+    if (!dead && h_lo < h_hi) {
+        const float depth = s_d[d];
+        const ColumnTerms ct = column_terms(T, s_u[col], depth);
+#pragma unroll 2
+        for (int h = h_lo; h < h_hi; ++h) {
+            float p[3];
+            ego_point(T, ct, s_v[h], depth, p);                               // fiery.py:199-205
+            const float ax = __fsub_rn(p[0], offx), ay = __fsub_rn(p[1], offy), az = __fsub_rn(p[2], offz);
+            const float sx = POW2 ? __fmul_rn(ax, kx) : __fdiv_rn(ax, kx);    // fiery.py:236 (x scale exact when res is 2^k)
+            const float sy = POW2 ? __fmul_rn(ay, ky) : __fdiv_rn(ay, ky);
+            const int rank = static_cast<int>(sx) * Y + static_cast<int>(sy); // truncation, fiery.py:237,252-256
+            const int cur = select_pillar(sx, sy, az, Xf, Yf, z_lo, z_hi, rank);   // mask, fiery.py:240-247
+            if (h == h_lo) first = cur;
+            else if (cur != prev) run_ends(h, prev, cur);
+            prev = cur;
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const bool change = row > 0 && c[j] != p[j];
-            if (change) {
-                chg |= 1u << j;
-                if (p[j] >= 0) fl |= 1u << j;
-            }
-            if (touched && (row == 0 || change) && c[j] >= 0) touched[c[j]] = 0x0f;   // one bit per channel quarter
+    }
+    const int before = __shfl_up_sync(0xffffffffu, prev, 1);   // last pillar of the previous row range of this pair
+    if (h_lo < h_hi) {
+        if (rs > 0 && split) {
+            if (first != before) run_ends(h_lo, before, first);
+        } else if (touched && first >= 0) {
+            touched[first] = 0x0f;                                  // row 0 starts a run
         }
-        s_ev[unit * 32 + row] = static_cast<unsigned short>(chg | (fl << 8));
+        if (h_hi == hh) tab[(hh - 1) * (COLS_NU * 8)] = prev;       // the run that reaches the last row
     }
 }
 
@@ -252,9 +252,10 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
         if (tid < WT) s_u[tid] = (w0 + tid < P.ww) ? P.fu[w0 + tid] : 0.f;
         if (tid >= 32 && tid < 64) s_v[tid - 32] = P.fv[min(tid - 32, hh - 1)];
         if (tid >= 64 && tid < 64 + COLS_DPAD) s_d[tid - 64] = (tid - 64 < P.D) ? P.fd[tid - 64] : 0.f;
+        unsigned* s_ev = reinterpret_cast<unsigned*>(smem + L.off_ev);
+        for (int i = tid; i < COLS_NU * COLS_EVS; i += NT) s_ev[i] = 0u;
     }
-    __syncthreads();                                  // mbarrier init visible before anyone polls it
-    // one lane composes R @ K^-1 (fiery.py:203) while the TMA is in flight and the others run the softmax
+    // one lane composes R @ K^-1 (fiery.py:203); the head tile stays in flight through the whole geometry phase
     if (tid == NT - 1) {
         CameraTransform T;
         load_camera(P.calib_mode, P.calib_a, P.calib_b, img, T);
@@ -264,13 +265,14 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
 #pragma unroll
         for (int i = 0; i < 3; ++i) s_cam[9 + i] = T.t[i];
     }
+    __syncthreads();                                  // constants, camera and the mbarrier are set up
+    {
+        unsigned char* touched = P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
+        if (P.grid.pow2[0] && P.grid.pow2[1]) stage_geometry_cols<true, NT>(P, L, smem, w0, touched);
+        else stage_geometry_cols<false, NT>(P, L, smem, w0, touched);
+    }
     mbar_wait(bar, 0);                                // head tile has landed
     softmax_cols<NT>(P, L, smem);
-    __syncthreads();
-    if (P.grid.pow2[0] && P.grid.pow2[1]) stage_pillars_cols<true, NT>(P, L, smem, w0);
-    else stage_pillars_cols<false, NT>(P, L, smem, w0);
-    __syncthreads();
-    stage_events_cols<NT>(L, smem, P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr);
     __syncthreads();
 
     // ---- pooling: thread = (unit of 2 depths, 4 columns, channels CPL*cl .. CPL*cl + CPL-1) ---------------------------
@@ -280,7 +282,7 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
     const float* cp = reinterpret_cast<const float*>(smem + L.off_ctx) + cl * WT;
     const int* plp = reinterpret_cast<const int*>(smem + L.off_pillar) + unit * 8 - COLS_NU * 8;       // row h-1
     char* out = reinterpret_cast<char*>(P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cl * CPL);
-    const unsigned short* evp = reinterpret_cast<const unsigned short*>(smem + L.off_ev) + unit * 32;
+    const unsigned* evp = reinterpret_cast<const unsigned*>(smem + L.off_ev) + unit * COLS_EVS + 1;      // row h+1
 
     unsigned long long acc[CPL][2][2];                // [channel k][depth dd][column pair]
 #pragma unroll
@@ -291,8 +293,8 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
     // otherwise diverge on every event).  Both are fetched one row ahead: the chain load -> reduce -> branch is long.
     unsigned own = 0, mw = 0;                         // row 0 starts every run
 #pragma unroll 2
-    for (int h = 0; h < hh; ++h, pp += COLS_DPAD * WT, cp += 64 * WT, plp += COLS_NU * 8) {
-        const unsigned own_next = evp[h + 1 < hh ? h + 1 : 0];       // row 0 holds no event
+    for (int h = 0; h < hh; ++h, pp += COLS_DPAD * WT, cp += 64 * WT, plp += COLS_NU * 8, ++evp) {
+        const unsigned own_next = *evp;                               // the word after the last row stays 0
         if (mw) {
             if (mw & 0x0fu) {
                 flush_slot<CPL, 0, 0>(acc, mw, own, plp, out); flush_slot<CPL, 0, 1>(acc, mw, own, plp, out);
