@@ -226,6 +226,29 @@ def test_graph_capture_and_host_pipeline_match_eager():
     assert O.normwise_error(out1, out) < 1e-6
 
 
+def test_row_order_of_the_frustum_is_not_assumed():
+    """The kernels pool along image columns but evaluate the geometry of every row: nothing may rely on the frustum's row
+    coordinates being sorted (fiery.py:122 makes them a linspace).  A frustum with permuted rows must give the lift of
+    exactly that frustum."""
+    cfg = LiftConfig(**{**CONFIGS["cfg2_static_lss"].__dict__, "frames": 2})
+    dev = _dev()
+    K, E = make_calibration(cfg, seed=17)
+    head = torch.from_numpy(make_head(cfg, seed=17))
+    lift = LiftSplat.from_config(cfg).to(dev)
+    oracle = O.LiftOracle.from_config(cfg)
+    h = oracle.frustum.shape[1]
+    perm = torch.from_numpy(np.random.default_rng(3).permutation(h))
+    assert not bool((perm[1:] > perm[:-1]).all())
+    oracle.frustum = oracle.frustum[:, perm].contiguous()
+    lift.frustum.data = lift.frustum.data[:, perm.to(dev)].contiguous()
+    lift._consts = None
+    with torch.no_grad():
+        got = lift(head.to(dev), torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)).cpu()
+    want = oracle.lift_exact(head, torch.from_numpy(K), torch.from_numpy(E))
+    assert O.normwise_error(got, want) < TOL
+    assert O.max_abs_scaled_error(got, want) < 1e-4
+
+
 def test_reference_call_site_signature_and_amp_head():
     """fiery_b200.lift.calculate_birds_eye_view_features has the signature and return shape of
     Fiery.calculate_birds_eye_view_features (fiery/models/fiery.py:275-286): x (b,s,n,3,H,W) -> (b,s,C,X,Y).  The stand-in
