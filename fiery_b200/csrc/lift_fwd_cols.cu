@@ -1,26 +1,33 @@
-// Forward lift, column-packed tile kernel.
+// Forward lift, the tile kernel: geometry + depth softmax + depth x context outer product + pillar pooling in one kernel; the
+// frustum volume (124 MB/frame in the reference, fiery/models/encoder.py:100) never leaves the SM.
 //
-// Same job and same arithmetic as lift_forward_kernel (lift_fwd.cu): get_geometry (fiery.py:193-208), depth softmax x
-// context outer product (encoder.py:98-100) and the voxel pooling of projection_to_birds_eye_view (fiery.py:221-273) for one
-// tile = one camera image x 4 feature columns x all rows x all depths x all channels, accumulated with vector reductions into
-// the channel-last accumulator.  What differs is the shared-memory layout, chosen so that NOTHING is transposed:
+// get_geometry (fiery.py:193-208), depth softmax x context outer product (encoder.py:98-100) and the voxel pooling of
+// projection_to_birds_eye_view (fiery.py:221-273) for one tile = one camera image x 4 feature columns x all rows x all depths x
+// all channels.
+//
+// Observation the kernel is built on: at fixed (camera, column, depth) the h image rows of a column fall into one BEV pillar,
+// or a handful, because Z is collapsed (Z_BOUND has one cell) and cameras are close to level.  So the reference's global
+// argsort + cumsum (fiery.py:257, geometry.py:289) becomes a register-resident *segmented* sum along the image column: a
+// thread walks the rows and only when the pillar changes (a precomputed event bit) does it flush its partial sum with one
+// vector reduction (red.global.add.v2.f32) into a channel-last BEV accumulator.  The 32 lanes of a warp cover the 64 channels
+// of a pillar, so each flush is two full 128-byte lines.  ~17k column segments per frame reach L2 instead of 453k points.
+//
+// The shared-memory layout is chosen so that NOTHING is transposed:
 //
 //   * the two TMA loads deliver the tile as  prob[row][depth][col4]  and  ctx[row][k][cl][col4]  (channel CPL*cl + k; the
 //     channel split is a 5-D tensor map, so the permutation is done by the copy engine).  One 16-byte shared load is then
 //     "4 adjacent columns of one (row, depth)" or "... of one (row, channel)";
 //   * a thread owns 2 depths x 4 columns x CPL channels, held as packed pairs of ADJACENT COLUMNS, so the outer product is
 //     4*CPL FFMA2 per row whose operands are exactly the register pairs the loads return;
-//   * the softmax runs in place on prob (lane = (depth mod 8, column): conflict free, reductions by shuffle) while one lane
-//     composes the camera matrix;
-//   * run ends are detected warp-uniformly (one 16-bit load + one warp reduction per row, fetched a row ahead).
+//   * the geometry (pillar of every point, reduced on the fly to run-end events) is evaluated while the TMA is in flight;
+//   * the softmax runs in place on prob (lane = (depth mod 8, column): conflict free, reductions by shuffle);
+//   * run ends are detected warp-uniformly (one 32-bit load + one warp reduction per row, fetched a row ahead).
 #include "lift_tile.cuh"
 
 namespace fiery {
 
 constexpr int COLS_DPAD = 48;                 // depth slots (D <= 48)
-constexpr int COLS_NU = COLS_DPAD / 2;        // units of 2 depths: one per half-warp
-constexpr int COLS_NT = COLS_NU * 16;         // 384 threads
-constexpr int COLS_NW = COLS_NT / 32;
+constexpr int COLS_NU = COLS_DPAD / 2;        // units of 2 depths: the 64 / CPL lanes of a unit own one each
 constexpr int COLS_EVS = 33;                  // event words per unit: rows 0..31 + one that stays 0
 
 struct HeadMapsCols {
@@ -351,16 +358,16 @@ static int launch_forward_cols_t(const HeadMapsCols& maps, const LiftParams& P, 
     return FIERY_OK;
 }
 
-// variant: 42 = 4 channels per lane, 2 tiles per SM; 43 = 4 channels, 3 tiles; 22 = 2 channels per lane (768 threads), 2 tiles
-int launch_forward_cols(const LiftParams& P, const void* head, int variant, cudaStream_t stream) {
+// Measured on B200, 8 frames (profiles/r01_notes.md): CPL = 2 with two 768-thread tiles per SM (40 registers, 48 resident
+// warps) 51.2 us; CPL = 4 with three 384-thread tiles (56 registers, 36 warps) 51.4-53.8 us; CPL = 4 with two tiles (73
+// registers, 24 warps) 56.0 us.  The kernel is bound by instruction issue and latency, so resident warps win.
+int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stream) {
     FIERY_REQUIRE(P.hh <= 32, "feat_h=%d not supported by this build (<= 32)", P.hh);
     FIERY_REQUIRE(P.C == 64 && P.D <= COLS_DPAD, "column kernel: C=%d D=%d not supported", P.C, P.D);
     HeadMapsCols maps;
-    const int rc = encode_head_maps_cols(&maps, head, P, variant == 22 ? 2 : 4);
+    const int rc = encode_head_maps_cols(&maps, head, P, 2);
     if (rc != FIERY_OK) return rc;
-    if (variant == 22) return launch_forward_cols_t<2, 2>(maps, P, stream);
-    if (variant == 43) return launch_forward_cols_t<4, 3>(maps, P, stream);
-    return launch_forward_cols_t<4, 2>(maps, P, stream);
+    return launch_forward_cols_t<2, 2>(maps, P, stream);
 }
 
 }  // namespace fiery

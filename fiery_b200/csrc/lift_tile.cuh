@@ -1,4 +1,4 @@
-// Tile staging shared by the forward and backward lift kernels.
+// Tile staging of the backward lift kernel (the forward kernel, lift_fwd_cols.cu, has its own transposition-free layout).
 //
 // Work unit ("tile"): one camera image of one frame, WT = 4 adjacent feature-map columns, all h rows, all D depth
 // bins, all C channels.  A tile is fetched from the NCHW head tensor (fiery/models/encoder.py:96 output) with 3-D TMA
@@ -49,7 +49,7 @@ struct TileLayout {
 
     int hh, C, PX;                               // PX = hh * WT pixels per tile
     // byte offsets into dynamic shared memory
-    int off_bar, off_cam, off_brk, off_u, off_v, off_d, off_red, off_prob, off_ctx, off_pillar, off_chg, off_ev, total;
+    int off_bar, off_cam, off_brk, off_u, off_v, off_d, off_red, off_prob, off_ctx, off_pillar, off_chg, total;
 
     __host__ __device__ TileLayout(int hh_, int C_) : hh(hh_), C(C_), PX(hh_ * WT) {
         int o = 0;
@@ -59,13 +59,12 @@ struct TileLayout {
         off_u = o;      o += WT * 4;
         off_d = o;      o += DPAD * 4;
         off_v = o;      o += ((hh + 3) & ~3) * 4;
-        // softmax partial max / sum per (depth group of 16, pixel); dead after transform_tile, so the run-end tables, which
+        // softmax partial max / sum per (depth group of 16, pixel); dead after transform_tile, so the change bits, which
         // are written after the barrier that follows stage_pillars, share the bytes
         const int red_bytes = 2 * (DPAD / 16) * PX * 4;
         const int chg_bytes = (PX * DBLKS + 15) & ~15;
-        const int ev_bytes = NWARPS * 32 * 4;    // forward: per (warp, row) run-end events, see stage_events
-        off_red = o;    off_chg = o;    off_ev = o + chg_bytes;
-        o += (red_bytes > chg_bytes + ev_bytes ? red_bytes : chg_bytes + ev_bytes);
+        off_red = o;    off_chg = o;
+        o += (red_bytes > chg_bytes ? red_bytes : chg_bytes);
         o = (o + 127) & ~127;
         const int prob_raw = DPAD * PX * 4, prob_t = PX * PS * 4;
         off_prob = o;   o += (prob_raw > prob_t ? prob_raw : prob_t);
@@ -177,47 +176,6 @@ __device__ __forceinline__ void stage_change_bits(const TileLayout<DBLKS>& L, un
         }
         s_chg[item] = static_cast<unsigned char>(m);
         if (m) atomicOr(s_brk + (pix / L.hh) * DBLKS + dblk, 1u << row);
-    }
-}
-
-// Forward run-end events.  ev[warp][row] (one 32-bit word, row < 32): byte 0 / 1 = bit j set <=> depth 8*dblk+j of the warp's
-// first / second unit (half-warp) changes pillar between row-1 and row; byte 2 / 3 = the same bits restricted to runs that end
-// on a valid pillar (they must be flushed; the others are only cleared).  Also marks every pillar that starts a run in the
-// `touched` map of the layout pass, so that the pooling loop itself only issues reductions.
-template <int DBLKS>
-__device__ __forceinline__ void stage_events(const TileLayout<DBLKS>& L, unsigned char* smem, unsigned char* touched) {
-    constexpr int DPAD = TileLayout<DBLKS>::DPAD;
-    const int* s_pillar = reinterpret_cast<const int*>(smem + L.off_pillar);
-    unsigned char* s_ev = smem + L.off_ev;
-    for (int item = threadIdx.x; item < WT * DBLKS * 32; item += blockDim.x) {
-        const int row = item & 31;
-        const int unit = item >> 5;                 // wt * DBLKS + dblk, the pooling loop's numbering
-        const int wt = unit / DBLKS, dblk = unit % DBLKS;
-        unsigned chg = 0, fl = 0;
-        if (row < L.hh) {
-            const int pix = wt * L.hh + row;
-            const int4* cur = reinterpret_cast<const int4*>(s_pillar + pix * DPAD + dblk * 8);
-            const int4 c0 = cur[0], c1 = cur[1];
-            const int c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            int p[8];
-            if (row > 0) {
-                const int4* prv = reinterpret_cast<const int4*>(s_pillar + (pix - 1) * DPAD + dblk * 8);
-                const int4 p0 = prv[0], p1 = prv[1];
-                p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const bool starts = row == 0 || c[j] != p[j];
-                if (row > 0 && starts) {
-                    chg |= 1u << j;
-                    if (p[j] >= 0) fl |= 1u << j;
-                }
-                if (touched && starts && c[j] >= 0) touched[c[j]] = 0x0f;     // one bit per channel quarter of the layout pass
-            }
-        }
-        unsigned char* e = s_ev + ((unit >> 1) * 32 + row) * 4 + (unit & 1);
-        e[0] = static_cast<unsigned char>(chg);
-        e[2] = static_cast<unsigned char>(fl);
     }
 }
 
