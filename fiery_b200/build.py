@@ -26,6 +26,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_flags():
+    """FIERY_NVCC_EXTRA: extra nvcc flags for experiment builds (e.g. -DFIERY_COLS_AB for tools/gpu_ab.sh); part of the stamp."""
+    return os.environ.get("FIERY_NVCC_EXTRA", "").split()
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):
@@ -41,7 +46,7 @@ def _source_hash() -> str:
         with open(f, "rb") as fh:
             h.update(f.encode())
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + _extra_flags()).encode())
     return h.hexdigest()
 
 
@@ -61,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"], "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"], *_extra_flags(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)

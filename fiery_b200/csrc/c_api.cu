@@ -88,7 +88,8 @@ int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams
     encode_tiled_fn fn = get_encode_fn();
     if (!fn) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     const size_t es = 4;
-    const cuuint64_t ww = P.ww, hh = P.hh, n_images = static_cast<cuuint64_t>(P.n_frames) * P.n_cameras;
+    // the image coordinate of a tile is absolute (frame0 * n_cameras + ...): the map spans every image up to this launch's last
+    const cuuint64_t ww = P.ww, hh = P.hh, n_images = static_cast<cuuint64_t>(P.frame0 + P.n_frames) * P.n_cameras;
     const cuuint64_t plane = ww * hh * es, image = plane * P.head_channels;
     FIERY_REQUIRE((reinterpret_cast<uintptr_t>(head) & 15) == 0 && (plane * (P.use_depth ? P.D : 0)) % 16 == 0,
                   "head tensor (or its context slice) is not 16-byte aligned");
@@ -114,6 +115,22 @@ int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled (context, 5-D) failed with CUresult %d", (int)r);
+    return FIERY_OK;
+}
+
+// NCHW output (frames, C, X*Y) as a 3-D map, innermost the pillar axis; the layout pass stores (box_pillars x C) blocks into it
+int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels, int n_frames, int box_pillars, int box_channels) {
+    encode_tiled_fn fn = get_encode_fn();
+    if (!fn) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    FIERY_REQUIRE((reinterpret_cast<uintptr_t>(bev) & 15) == 0 && pillars % 4 == 0, "BEV output is not 16-byte aligned / pitched");
+    FIERY_REQUIRE(channels <= 256 && box_pillars <= 256, "BEV map: box too large");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(pillars), static_cast<cuuint64_t>(channels), static_cast<cuuint64_t>(n_frames)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(pillars) * 4, static_cast<cuuint64_t>(pillars) * channels * 4};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(box_pillars), static_cast<cuuint32_t>(box_channels), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, bev, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled (BEV output) failed with CUresult %d", (int)r);
     return FIERY_OK;
 }
 

@@ -27,8 +27,11 @@
 namespace fiery {
 
 constexpr int COLS_DPAD = 48;                 // depth slots (D <= 48)
-constexpr int COLS_NU = COLS_DPAD / 2;        // units of 2 depths: the 64 / CPL lanes of a unit own one each
+constexpr int COLS_NPAIR = COLS_DPAD * WT;    // (depth, column) pairs of a tile: each is one image column of points
 constexpr int COLS_EVS = 33;                  // event words per unit: rows 0..31 + one that stays 0
+// A "unit" is DD adjacent depths x the 4 columns of the tile (4*DD pairs = "slots"); the 64 / CPL lanes of a unit own CPL
+// channels each.  DD trades shared-memory traffic for registers: per image row a unit reads the whole 1 KB context row of the
+// tile, so the tile's context traffic is (48 / DD) KB per row.
 
 struct HeadMapsCols {
     CUtensorMap depth;    // 4-D (w, d, h, image), box (4, 48, h, 1)
@@ -38,7 +41,7 @@ struct HeadMapsCols {
 struct ColsLayout {
     int hh, C;
     int off_bar, off_cam, off_u, off_v, off_d, off_ev, off_prob, off_ctx, off_pillar, total;
-    __host__ __device__ ColsLayout(int hh_, int C_) : hh(hh_), C(C_) {
+    __host__ __device__ ColsLayout(int hh_, int C_, int n_units) : hh(hh_), C(C_) {
         int o = 0;
         off_bar = o;    o += 16;
         off_cam = o;    o += 12 * 4;
@@ -46,13 +49,13 @@ struct ColsLayout {
         off_v = o;      o += 32 * 4;
         off_d = o;      o += COLS_DPAD * 4;
         o = (o + 15) & ~15;
-        off_ev = o;     o += COLS_NU * COLS_EVS * 4;   // run-end events: [unit][row], see stage_geometry_cols
+        off_ev = o;     o += n_units * COLS_EVS * 4;   // run-end events: [unit][row], see stage_geometry_cols
         o = (o + 127) & ~127;
         off_prob = o;   o += hh * COLS_DPAD * WT * 4;
         o = (o + 127) & ~127;
         off_ctx = o;    o += hh * C * WT * 4;
         o = (o + 127) & ~127;
-        off_pillar = o; o += hh * COLS_NU * 8 * 4;     // [row][unit][j = dd*4 + col]
+        off_pillar = o; o += hh * COLS_NPAIR * 4;      // [row][pair = depth*4 + col]
         total = o;
     }
 };
@@ -82,17 +85,17 @@ __device__ __forceinline__ void clear_half(unsigned long long& v, unsigned keep)
 
 // Geometry of the tile: the pillar (rank, fiery.py:236-256; -1 = masked) of every point, evaluated with the reference
 // arithmetic, reduced on the fly to what the pooling loop consumes:
-//   ev[unit][row]      bit j (j = dd*4 + col: depth 2*unit + dd, column col) set <=> pair j changes pillar between row-1 and
-//                      row; bit 8+j: ... and the run that ends sits on a valid pillar (it must be flushed, the others are
-//                      only cleared)
-//   pillar[row][unit][j]  written only where it is read: the last row of every run
+//   ev[unit][row]      bit j (slot j = dd*4 + col: depth DD*unit + dd, column col) set <=> pair j changes pillar between
+//                      row-1 and row; bit 4*DD + j: ... and the run that ends sits on a valid pillar (it must be flushed, the
+//                      others are only cleared)
+//   pillar[row][pair]  written only where it is read: the last row of every run
 //   touched[pillar]    the layout pass's map of pillars that receive something, marked at every run start
 // thread = (pair, row range); the NRS ranges of a pair sit in adjacent lanes and hand their last pillar to the next range.
-template <bool POW2, int NT>
+template <bool POW2, int NT, int DD>
 __device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem, int w0,
                                                     unsigned char* touched) {
-    constexpr int NPAIR = COLS_NU * 8;
-    constexpr int NRS = NT / NPAIR;
+    constexpr int NRS = NT / COLS_NPAIR >= 4 ? 4 : (NT / COLS_NPAIR >= 2 ? 2 : 1);
+    static_assert(NT >= COLS_NPAIR, "one thread per (depth, column) pair at least");
     const float* s_cam = reinterpret_cast<const float*>(smem + L.off_cam);
     const float* s_u = reinterpret_cast<const float*>(smem + L.off_u);
     const float* s_v = reinterpret_cast<const float*>(smem + L.off_v);
@@ -111,18 +114,19 @@ __device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const C
     const int Y = P.grid.Y;
     const int hh = L.hh;
     const int pair = threadIdx.x / NRS, rs = threadIdx.x % NRS;
-    const int unit = pair >> 3, j = pair & 7;
-    const int d = unit * 2 + (j >> 2), col = j & 3;
+    const bool idle = pair >= COLS_NPAIR;                    // NT is not always a multiple of the pair count
+    const int d = idle ? 0 : pair >> 2, col = pair & 3;
+    const int unit = d / DD, j = (d % DD) * 4 + col;
     const bool split = hh >= 2 * NRS;                       // short columns: one lane of the pair walks all rows
-    const int h_lo = split ? (hh * rs) / NRS : 0;
-    const int h_hi = split ? (hh * (rs + 1)) / NRS : (rs == 0 ? hh : 0);
+    const int h_lo = idle ? 0 : (split ? (hh * rs) / NRS : 0);
+    const int h_hi = idle ? 0 : (split ? (hh * (rs + 1)) / NRS : (rs == 0 ? hh : 0));
     const bool dead = d >= P.D || w0 + col >= P.ww;
 
     unsigned* ev = s_ev + unit * COLS_EVS;
-    int* tab = s_pillar + unit * 8 + j;
+    int* tab = s_pillar + (idle ? 0 : pair);
     auto run_ends = [&](int h, int before, int now) {        // rows h-1 | h lie in different pillars
-        atomicOr(ev + h, (1u << j) | (before >= 0 ? (0x100u << j) : 0u));
-        if (before >= 0) tab[(h - 1) * (COLS_NU * 8)] = before;
+        atomicOr(ev + h, (1u << j) | (before >= 0 ? (1u << (4 * DD + j)) : 0u));
+        if (before >= 0) tab[(h - 1) * COLS_NPAIR] = before;
         if (touched && now >= 0) touched[now] = 0x0f;       // one bit per channel quarter of the layout pass
     };
 
@@ -151,7 +155,7 @@ __device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const C
         } else if (touched && first >= 0) {
             touched[first] = 0x0f;                                  // row 0 starts a run
         }
-        if (h_hi == hh) tab[(hh - 1) * (COLS_NU * 8)] = prev;       // the run that reaches the last row
+        if (h_hi == hh) tab[(hh - 1) * COLS_NPAIR] = prev;          // the run that reaches the last row
     }
 }
 
@@ -210,29 +214,44 @@ __device__ __forceinline__ void red_channels_if(char* dst, const float (&v)[CPL]
 // the ending run reduce their channels into the accumulator and restart.  The "+ 0.0f" copies are real instructions on
 // purpose: they gather the values into the consecutive registers the vector reduction needs HERE, instead of letting the
 // register allocator keep the accumulators in that order and un-shuffle them around every FFMA2.
-template <int CPL, int DD, int COL>
-__device__ __forceinline__ void flush_slot(unsigned long long (&acc)[CPL][2][2], unsigned mw, unsigned own, const int* plp, char* out) {
-    constexpr int j = DD * 4 + COL;
+template <int CPL, int DD, int SD, int COL>
+__device__ __forceinline__ void flush_slot(unsigned long long (&acc)[CPL][DD][2], unsigned mw, unsigned own, unsigned flush,
+                                           const int* plp, char* out) {
+    constexpr int j = SD * 4 + COL;
     if (mw & (1u << j)) {
         const unsigned pl = static_cast<unsigned>(plp[j]);
         float v[CPL];
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) v[k] = __fadd_rn(half_of<COL & 1>(acc[k][DD][COL >> 1]), 0.0f);
-        red_channels_if<CPL>(out + static_cast<size_t>(pl) * (64 * 4), v, own & (0x100u << j));
+        for (int k = 0; k < CPL; ++k) v[k] = __fadd_rn(half_of<COL & 1>(acc[k][SD][COL >> 1]), 0.0f);
+        red_channels_if<CPL>(out + static_cast<size_t>(pl) * (64 * 4), v, flush & (1u << j));
         const unsigned keep = ((own >> j) & 1u) - 1u;          // 0 where my run ends, ~0 otherwise
 #pragma unroll
-        for (int k = 0; k < CPL; ++k) clear_half<COL & 1>(acc[k][DD][COL >> 1], keep);
+        for (int k = 0; k < CPL; ++k) clear_half<COL & 1>(acc[k][SD][COL >> 1], keep);
     }
 }
 
-// CPL channels per lane: 4 -> a unit is a half-warp, 384 threads; 2 -> a unit is a warp, 768 threads
-template <int CPL, int MINB>
-__global__ void __launch_bounds__(COLS_NU * (64 / CPL), MINB)
+template <int CPL, int DD, int SD>
+__device__ __forceinline__ void flush_depth(unsigned long long (&acc)[CPL][DD][2], unsigned mw, unsigned own, unsigned flush,
+                                            const int* plp, char* out) {
+    if (mw & (0xfu << (4 * SD))) {
+        flush_slot<CPL, DD, SD, 0>(acc, mw, own, flush, plp, out); flush_slot<CPL, DD, SD, 1>(acc, mw, own, flush, plp, out);
+        flush_slot<CPL, DD, SD, 2>(acc, mw, own, flush, plp, out); flush_slot<CPL, DD, SD, 3>(acc, mw, own, flush, plp, out);
+    }
+    if constexpr (SD + 1 < DD) flush_depth<CPL, DD, SD + 1>(acc, mw, own, flush, plp, out);
+}
+
+// CPL channels per lane, DD depths per unit: a unit is 64 / CPL lanes, a tile 48 / DD units.
+//   CPL 2, DD 2: 768 threads (a unit is a warp)      CPL 2, DD 4: 384 threads      CPL 4, DD 4: 192 threads (a unit is a half-warp)
+template <int CPL, int DD, int MINB>
+__global__ void __launch_bounds__((COLS_DPAD / DD) * (64 / CPL), MINB)
 lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const LiftParams P) {
     constexpr int LPU = 64 / CPL;                     // lanes per unit
-    constexpr int NT = COLS_NU * LPU;
+    constexpr int NU = COLS_DPAD / DD;                // units per tile
+    constexpr int NT = NU * LPU;
+    constexpr int SLOTS = 4 * DD;
+    static_assert(COLS_DPAD % DD == 0 && SLOTS <= 16 && (LPU == 16 || LPU == 32), "unsupported unit shape");
     extern __shared__ __align__(128) unsigned char smem[];
-    const ColsLayout L(P.hh, P.C);
+    const ColsLayout L(P.hh, P.C, NU);
     const int wtile = blockIdx.x % P.n_wtiles;
     const int img_local = blockIdx.x / P.n_wtiles;    // (frame, camera) within this launch's chunk of frames
     const int img = P.frame0 * P.n_cameras + img_local;
@@ -260,7 +279,7 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
         if (tid >= 32 && tid < 64) s_v[tid - 32] = P.fv[min(tid - 32, hh - 1)];
         if (tid >= 64 && tid < 64 + COLS_DPAD) s_d[tid - 64] = (tid - 64 < P.D) ? P.fd[tid - 64] : 0.f;
         unsigned* s_ev = reinterpret_cast<unsigned*>(smem + L.off_ev);
-        for (int i = tid; i < COLS_NU * COLS_EVS; i += NT) s_ev[i] = 0u;
+        for (int i = tid; i < NU * COLS_EVS; i += NT) s_ev[i] = 0u;
     }
     // one lane composes R @ K^-1 (fiery.py:203); the head tile stays in flight through the whole geometry phase
     if (tid == NT - 1) {
@@ -275,58 +294,57 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
     __syncthreads();                                  // constants, camera and the mbarrier are set up
     {
         unsigned char* touched = P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
-        if (P.grid.pow2[0] && P.grid.pow2[1]) stage_geometry_cols<true, NT>(P, L, smem, w0, touched);
-        else stage_geometry_cols<false, NT>(P, L, smem, w0, touched);
+        if (P.grid.pow2[0] && P.grid.pow2[1]) stage_geometry_cols<true, NT, DD>(P, L, smem, w0, touched);
+        else stage_geometry_cols<false, NT, DD>(P, L, smem, w0, touched);
     }
     mbar_wait(bar, 0);                                // head tile has landed
     softmax_cols<NT>(P, L, smem);
     __syncthreads();
 
-    // ---- pooling: thread = (unit of 2 depths, 4 columns, channels CPL*cl .. CPL*cl + CPL-1) ---------------------------
+    // ---- pooling: thread = (unit of DD depths, 4 columns, channels CPL*cl .. CPL*cl + CPL-1) ---------------------------
     const int unit = tid / LPU;
     const int cl = tid % LPU;
-    const float* pp = reinterpret_cast<const float*>(smem + L.off_prob) + unit * 2 * WT;
+    const float* pp = reinterpret_cast<const float*>(smem + L.off_prob) + unit * DD * WT;
     const float* cp = reinterpret_cast<const float*>(smem + L.off_ctx) + cl * WT;
-    const int* plp = reinterpret_cast<const int*>(smem + L.off_pillar) + unit * 8 - COLS_NU * 8;       // row h-1
+    const int* plp = reinterpret_cast<const int*>(smem + L.off_pillar) + unit * SLOTS - COLS_NPAIR;          // row h-1
     char* out = reinterpret_cast<char*>(P.accum + static_cast<size_t>(frame) * P.pillars * P.C + cl * CPL);
-    const unsigned* evp = reinterpret_cast<const unsigned*>(smem + L.off_ev) + unit * COLS_EVS + 1;      // row h+1
+    const unsigned* evp = reinterpret_cast<const unsigned*>(smem + L.off_ev) + unit * COLS_EVS + 1;         // row h+1
 
-    unsigned long long acc[CPL][2][2];                // [channel k][depth dd][column pair]
+    unsigned long long acc[CPL][DD][2];               // [channel k][depth dd][column pair]
 #pragma unroll
-    for (int k = 0; k < CPL; ++k) acc[k][0][0] = acc[k][0][1] = acc[k][1][0] = acc[k][1][1] = 0ull;
+    for (int k = 0; k < CPL; ++k)
+#pragma unroll
+        for (int dd = 0; dd < DD; ++dd) acc[k][dd][0] = acc[k][dd][1] = 0ull;
 
-    // own: bits 0-7 my runs that end at this row, bits 8-15 ... and must be flushed.  mw: slots that end a run anywhere in
-    // the warp -- a warp reduction, so every run-end branch is warp-uniform (half-warps that own different depths would
-    // otherwise diverge on every event).  Both are fetched one row ahead: the chain load -> reduce -> branch is long.
-    unsigned own = 0, mw = 0;                         // row 0 starts every run
+    // own: my slots whose run ends at this row, flush: ... and must be flushed.  mw: slots that end a run anywhere in the
+    // warp -- a warp reduction when two units share a warp, so every run-end branch is warp-uniform (half-warps that own
+    // different depths would otherwise diverge on every event).  All are fetched one row ahead: the chain load -> reduce ->
+    // branch is long.
+    unsigned own = 0, flush = 0, mw = 0;              // row 0 starts every run
 #pragma unroll 2
-    for (int h = 0; h < hh; ++h, pp += COLS_DPAD * WT, cp += 64 * WT, plp += COLS_NU * 8, ++evp) {
-        const unsigned own_next = *evp;                               // the word after the last row stays 0
-        if (mw) {
-            if (mw & 0x0fu) {
-                flush_slot<CPL, 0, 0>(acc, mw, own, plp, out); flush_slot<CPL, 0, 1>(acc, mw, own, plp, out);
-                flush_slot<CPL, 0, 2>(acc, mw, own, plp, out); flush_slot<CPL, 0, 3>(acc, mw, own, plp, out);
-            }
-            if (mw & 0xf0u) {
-                flush_slot<CPL, 1, 0>(acc, mw, own, plp, out); flush_slot<CPL, 1, 1>(acc, mw, own, plp, out);
-                flush_slot<CPL, 1, 2>(acc, mw, own, plp, out); flush_slot<CPL, 1, 3>(acc, mw, own, plp, out);
-            }
-        }
-        const ulonglong2 d0 = *reinterpret_cast<const ulonglong2*>(pp);           // depth 2u:   columns (0,1) (2,3)
-        const ulonglong2 d1 = *reinterpret_cast<const ulonglong2*>(pp + WT);      // depth 2u+1
+    for (int h = 0; h < hh; ++h, pp += COLS_DPAD * WT, cp += 64 * WT, plp += COLS_NPAIR, ++evp) {
+        const unsigned ev_next = *evp;                                // the word after the last row stays 0
+        if (mw) flush_depth<CPL, DD, 0>(acc, mw, own, flush, plp, out);
+        ulonglong2 dv[DD];
+#pragma unroll
+        for (int dd = 0; dd < DD; ++dd) dv[dd] = *reinterpret_cast<const ulonglong2*>(pp + dd * WT);   // columns (0,1) (2,3)
 #pragma unroll
         for (int k = 0; k < CPL; ++k) {
             const ulonglong2 c = *reinterpret_cast<const ulonglong2*>(cp + k * LPU * WT);   // channel CPL*cl + k
             // depth x context outer product (encoder.py:100), summed along the column
-            ffma2(acc[k][0][0], d0.x, c.x); ffma2(acc[k][0][1], d0.y, c.y);
-            ffma2(acc[k][1][0], d1.x, c.x); ffma2(acc[k][1][1], d1.y, c.y);
+#pragma unroll
+            for (int dd = 0; dd < DD; ++dd) {
+                ffma2(acc[k][dd][0], dv[dd].x, c.x);
+                ffma2(acc[k][dd][1], dv[dd].y, c.y);
+            }
         }
-        own = own_next;
-        mw = __reduce_or_sync(0xffffffffu, own & 0xffu);
+        own = ev_next & ((1u << SLOTS) - 1u);
+        flush = ev_next >> SLOTS;
+        mw = LPU == 32 ? own : __reduce_or_sync(0xffffffffu, own);
     }
     // the runs that reach the last row (plp now points at it)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < SLOTS; ++j) {
         const int pl = plp[j];
         float v[CPL];
 #pragma unroll
@@ -340,34 +358,57 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
 
 int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams& P, int channels_per_lane);
 
-template <int CPL, int MINB>
-static int launch_forward_cols_t(const HeadMapsCols& maps, const LiftParams& P, cudaStream_t stream) {
-    const ColsLayout L(P.hh, P.C);
+template <int CPL, int DD, int MINB>
+static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStream_t stream) {
+    constexpr int NU = COLS_DPAD / DD, NT = NU * (64 / CPL);
+    const ColsLayout L(P.hh, P.C, NU);
     static bool configured = false;
     if (!configured) {
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // ask for the full shared-memory carve-out (3 x 74 KB per SM for the reference shape)
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     FIERY_REQUIRE(L.total <= 227 * 1024, "tile needs %d bytes of shared memory", L.total);
+    HeadMapsCols maps;
+    const int rc = encode_head_maps_cols(&maps, head, P, CPL);
+    if (rc != FIERY_OK) return rc;
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
-    lift_forward_cols_kernel<CPL, MINB><<<static_cast<unsigned>(n_tiles), COLS_NU * (64 / CPL), L.total, stream>>>(maps, P);
+    lift_forward_cols_kernel<CPL, DD, MINB><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }
 
-// Measured on B200, 8 frames (profiles/r01_notes.md): CPL = 2 with two 768-thread tiles per SM (40 registers, 48 resident
-// warps) 51.2 us; CPL = 4 with three 384-thread tiles (56 registers, 36 warps) 51.4-53.8 us; CPL = 4 with two tiles (73
-// registers, 24 warps) 56.0 us.  The kernel is bound by instruction issue and latency, so resident warps win.
+// Measured on B200, 8 frames (profiles/r01_notes.md).  The pooling loop is bound by shared-memory wavefronts (a broadcast
+// LDS.128 costs 2, a 512-byte one 4) and the rest of the tile by instruction issue, so the shape of a unit is a trade between
+// context re-reads (48 / DD per row), registers (4 * CPL * DD accumulators) and resident warps.
 int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stream) {
     FIERY_REQUIRE(P.hh <= 32, "feat_h=%d not supported by this build (<= 32)", P.hh);
     FIERY_REQUIRE(P.C == 64 && P.D <= COLS_DPAD, "column kernel: C=%d D=%d not supported", P.C, P.D);
-    HeadMapsCols maps;
-    const int rc = encode_head_maps_cols(&maps, head, P, 2);
-    if (rc != FIERY_OK) return rc;
-    return launch_forward_cols_t<2, 2>(maps, P, stream);
+    // Unit shape, measured on B200 (profiles/r01_notes.md): DD = 3 (512 threads, 58 registers) is 7-8 % faster when the grid fills
+    // whole waves of 2 tiles per SM (9 frames: 55.3 vs 60.2 us, 12 frames at 400x200: 72.0 vs 77.1 us); DD = 2 (768 threads) is
+    // faster while tiles run alone on an SM, i.e. when the last wave is at most half full (8 frames: 52.3 vs 53.4 us).
+    int n_sm = 0, dev = 0;
+    FIERY_CUDA_CHECK(cudaGetDevice(&dev));
+    FIERY_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
+    const long long rem = n_tiles % (2ll * n_sm);
+    int variant = (rem > 0 && rem <= n_sm) ? 0 : 2;
+#ifdef FIERY_COLS_AB
+    // A/B builds only (tools/gpu_ab.sh): unit shape chosen per call
+    if (const char* e = getenv("FIERY_COLS_VARIANT")) variant = atoi(e) >= 0 ? atoi(e) : variant;
+    switch (variant) {
+        case 1: return launch_forward_cols_t<2, 4, 2>(P, head, stream);
+        case 4: return launch_forward_cols_t<4, 4, 3>(P, head, stream);
+        case 5: return launch_forward_cols_t<4, 2, 3>(P, head, stream);
+        case 6: return launch_forward_cols_t<4, 3, 3>(P, head, stream);
+        case 7: return launch_forward_cols_t<2, 4, 3>(P, head, stream);
+        default: break;
+    }
+#endif
+    if (variant == 2) return launch_forward_cols_t<2, 3, 2>(P, head, stream);
+    return launch_forward_cols_t<2, 2, 2>(P, head, stream);
 }
 
 }  // namespace fiery

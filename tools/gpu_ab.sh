@@ -1,11 +1,14 @@
 #!/bin/bash
-# A/B of the layout pass: separate re-zeroing kernels vs the fused 32-byte variant
+# A/B of an experiment build (python -m fiery_b200.build with FIERY_NVCC_EXTRA=-DFIERY_COLS_AB): unit shapes of the column tile
+# kernel x layout passes x stream chains (AB_COMBOS = "tile:pass:ctas:chains ..."), then the lift parity tests on the
+# requested combinations (AB_TEST, same format)
 mkdir -p gpurun_out
-for v in separate fused; do
-  FIERY_FINALIZE=$v timeout 600 python -m pytest tests/test_lift_gpu.py -m gpu -q --no-header -x 2>&1 | tail -2
-  FIERY_FINALIZE=$v timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
-  python -c "
-import json; d=json.load(open('gpurun_out/bench_$v.json')); print('$v', d['ms_per_step'], d['value'], d['roofline']['kernel_ms'], d['roofline']['lift_plus_finalize_ms'], d['value_eager'])" || tail -5 gpurun_out/bench_$v.err
+timeout 600 python tools/ab_forward.py cfg2_static_lss_b8 2>&1 | grep -E "^tile|^pass|Error|error" | cut -c1-260
+timeout 300 python tools/ab_forward.py cfg3_baseline 2>&1 | grep -E "^tile|^pass|Error|error" | cut -c1-260
+timeout 300 python tools/ab_forward.py cfg4_pon 2>&1 | grep -E "^tile|^pass|Error|error" | cut -c1-260
+timeout 300 python tools/ab_forward.py cfg2_static_lss 2>&1 | grep -E "^tile|^pass|Error|error" | cut -c1-260
+for combo in $AB_TEST; do
+  IFS=: read v f c ch <<< "$combo"
+  echo "== parity tests with tile variant $v, layout pass $f, $c CTAs/SM, $ch chains"
+  FIERY_COLS_VARIANT=$v FIERY_FINALIZE=$f FIERY_FINALIZE_CTAS=$c FIERY_CHAINS=$ch timeout 600 python -m pytest tests/test_lift_gpu.py -m gpu -q --no-header -x 2>&1 | tail -3
 done
-FIERY_FINALIZE=fused timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_fused.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
-grep -E "finalize|clear|lift_forward" gpurun_out/launches_fused.csv | awk -F, '{print $5, $NF}' | tail -8
