@@ -8,7 +8,7 @@ synthetic frames.  Prints ONE JSON line (rank 0).
 
   value      whole-job frames/s, inputs resident in HBM, through the public Python API (LiftSplat.forward -> C ABI)
   e2e        same metric with HOST (pinned) inputs and a host copy of the BEV inside the timed region
-  roofline   the dominant kernel (lift_forward_kernel) against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline   the dominant kernel (lift_forward_cols_kernel) against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the oracle's torch-CPU restatement of the reference op chain on this box's host cores, bounded sample
 
 `--impl reference` times that CPU restatement itself (the reference is pure PyTorch; /root/reference is not on the GPU
@@ -234,8 +234,8 @@ def main():
         return times
 
     # ---- value: device-resident inputs through the public API ----------------------------------------------------------
-    # LiftSplat.capture() records the forward lift (TMA descriptors + both kernels) into a CUDA graph once; a step is one
-    # replay.  The eager call (LiftSplat.forward) is timed too and reported as value_eager.
+    # LiftSplat.capture() records the forward lift (TMA descriptors + the tile-kernel / layout-pass chains of every frame
+    # group, forked over internal streams) into a CUDA graph once; a step is one replay.  The eager call (LiftSplat.forward) is timed too and reported as value_eager.
     def step_eager():
         with torch.no_grad():
             return lift(head_d, K_d, E_d)
@@ -288,7 +288,7 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline: the kernels of the step through the C ABI, events on their stream; NHWC mode runs lift_forward_kernel alone ----
+    # ---- roofline: the kernels of the step through the C ABI, events on their stream; NHWC mode runs lift_forward_cols_kernel alone ----
     lib = _lib.load()
     c = lift._constants(dev)
     stream = _stream_ptr(dev)
@@ -303,6 +303,9 @@ def main():
                                               stream), "fiery_lift_forward")
         return run, scratch
 
+    launches_per_step = int(lib.fiery_lift_forward_launches(
+        lift._desc(c, frames, cfg.n_cameras, torch.float32, _lib.CALIB_RAW,
+                   _lib.BEV_NHWC if args.layout == "channels_last" else _lib.BEV_NCHW)))
     out_nchw = torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
     acc_nhwc = torch.zeros((frames, X, Y, cfg.out_channels), dtype=torch.float32, device=dev)
     run_fused, _s1 = make_kernel_only(_lib.BEV_NCHW, out_nchw)
@@ -310,8 +313,8 @@ def main():
     for _ in range(3):
         run_fused()
         run_tiles()
-    t_both = timed_steps(run_fused, S)          # lift_forward_cols_kernel + finalize_clear_nchw_kernel
-    t_kernel = timed_steps(run_tiles, S)        # lift_forward_kernel alone (channel-last target)
+    t_both = timed_steps(run_fused, S)          # lift_forward_cols_kernel + finalize_tma_kernel chains (eager C-ABI call)
+    t_kernel = timed_steps(run_tiles, S)        # lift_forward_cols_kernel alone (channel-last target)
     barrier()
 
     # ---- the literal drop-in at fiery.py:261: VoxelsSumming on one frame's rank-sorted point features ------------------------
@@ -416,7 +419,8 @@ def main():
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(head_h.numel() * 4 + K_h.numel() * 4 + E_h.numel() * 4),
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},
-            "gpu_launches": (1 if args.layout == "channels_last" else 2) * S,   # lift tile kernel + layout/re-zeroing pass
+            # kernels of the timed `value` region: per step, one tile kernel (+ one layout pass) per frame group
+            "gpu_launches": launches_per_step * S,
             "roofline": {"bound": "hbm", "kernel": "lift_forward_cols_kernel", "achieved": achieved, "peak": peak,
                          "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(cfg.name),
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "lift_plus_finalize_ms": ms_both,

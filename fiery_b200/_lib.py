@@ -39,6 +39,7 @@ SIGNATURES = {
     "fiery_abi_version": (c_int32, []),
     "fiery_last_error": (c_char_p, []),
     "fiery_lift_scratch_bytes": (c_size_t, [POINTER(LiftDesc)]),
+    "fiery_lift_forward_launches": (c_int32, [POINTER(LiftDesc)]),
     "fiery_lift_forward": (c_int32, [POINTER(LiftDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p]),
     "fiery_lift_workspace_bytes": (c_size_t, [POINTER(LiftDesc)]),

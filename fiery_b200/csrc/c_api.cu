@@ -65,7 +65,7 @@ static int encode_view(CUtensorMap* map, const void* head, long long n_images, i
 
 int encode_head_maps(HeadMaps* maps, const void* head, int dtype, const LiftParams& P) {
     FIERY_REQUIRE(dtype == FIERY_DTYPE_F32, "TMA map: only fp32 head tensors are supported");
-    const long long n_images = static_cast<long long>(P.n_frames) * P.n_cameras;
+    const long long n_images = static_cast<long long>(P.frame0 + P.n_frames) * P.n_cameras;
     int rc = FIERY_OK;
     if (P.use_depth) {
         rc = encode_view(&maps->depth, head, n_images, P.head_channels, 0, P.D, P.hh, P.ww);
@@ -119,14 +119,14 @@ int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams
 }
 
 // NCHW output (frames, C, X*Y) as a 3-D map, innermost the pillar axis; the layout pass stores (box_pillars x C) blocks into it
-int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels, int n_frames, int box_pillars, int box_channels) {
+int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels, int n_frames, int box_pillars) {
     encode_tiled_fn fn = get_encode_fn();
     if (!fn) return set_error(FIERY_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     FIERY_REQUIRE((reinterpret_cast<uintptr_t>(bev) & 15) == 0 && pillars % 4 == 0, "BEV output is not 16-byte aligned / pitched");
     FIERY_REQUIRE(channels <= 256 && box_pillars <= 256, "BEV map: box too large");
     cuuint64_t dims[3] = {static_cast<cuuint64_t>(pillars), static_cast<cuuint64_t>(channels), static_cast<cuuint64_t>(n_frames)};
     cuuint64_t strides[2] = {static_cast<cuuint64_t>(pillars) * 4, static_cast<cuuint64_t>(pillars) * channels * 4};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(box_pillars), static_cast<cuuint32_t>(box_channels), 1};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(box_pillars), static_cast<cuuint32_t>(channels), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, bev, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -137,6 +137,7 @@ int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels
 // launchers defined next to their kernels
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch, cudaStream_t);
 int lift_chunk_frames(int n_frames, long long pillars, int channels);
+int lift_forward_launches(const LiftParams& P);
 int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, float* workspace, cudaStream_t);
 int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t);
 int launch_compose(int n, const float* K, const float* E, float* combined, float* translation, cudaStream_t);
@@ -193,6 +194,16 @@ FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
     const long long per_frame = static_cast<long long>(d->bev_x) * d->bev_y;
     const size_t pillars = static_cast<size_t>(lift_chunk_frames(d->n_frames, per_frame, d->channels)) * per_frame;   // one chunk of frames
     return pillars * d->channels * sizeof(float) + ((pillars + 15) & ~static_cast<size_t>(15));   // accumulator + touched map
+}
+
+FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* d) {
+    if (!d || d->n_frames <= 0 || d->n_cameras < 1 || d->feat_w < 1) return 0;
+    LiftParams P;
+    P.n_frames = d->n_frames; P.n_cameras = d->n_cameras; P.C = d->channels;
+    P.n_wtiles = (d->feat_w + WT - 1) / WT;
+    P.bev_layout = d->bev_layout;
+    P.pillars = static_cast<long long>(d->bev_x) * d->bev_y;
+    return lift_forward_launches(P);
 }
 
 FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* d) {

@@ -48,64 +48,6 @@ finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flag
     }
 }
 
-// 32-byte global accesses (sm_100: LDG/STG.256): one full L2 sector per access
-__device__ __forceinline__ void ldcg_256(const float* p, float4& a, float4& b) {
-    asm volatile("ld.global.cg.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
-}
-__device__ __forceinline__ void st_zero_256(float* p) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" :: "l"(p), "f"(0.0f) : "memory");
-}
-
-// The layout pass and the re-zeroing of the scratch in ONE kernel.  A thread takes four consecutive pillars x one quarter
-// of the channels (16): it loads its 4 x 64 bytes up front, transposes the 4 x 16 block in registers and writes sixteen
-// 16-byte streaming stores; a warp covers 128 pillars, i.e. 512 contiguous bytes per channel row.  The 64 bytes a thread
-// owns of every pillar row are moved as two full 32-byte sectors, so the zeroes that restore the scratch invariant are
-// whole-sector stores right behind the loads (16-byte stores to the same place doubled the kernel's time: partial-sector
-// writes; two separate re-zeroing kernels cost 14 us where this costs 11).  The touched byte of a pillar carries one bit
-// per channel quarter so the four quarter-blocks clear their bit independently.  Needs X*Y to be a multiple of 4.
-__global__ void __launch_bounds__(FIN_THREADS)
-finalize_clear_nchw_kernel(float* __restrict__ accum, unsigned* __restrict__ flags32, float* __restrict__ bev,
-                           long long pillars, int blocks_per_frame) {
-    constexpr int C = 64;
-    const int q = blockIdx.x & 3;                      // channel quarter
-    const int b = blockIdx.x >> 2;
-    const int frame = b / blocks_per_frame;
-    const long long p0 = (static_cast<long long>(b % blocks_per_frame) * FIN_THREADS + threadIdx.x) * 4;
-    if (p0 >= pillars) return;
-    unsigned* fw = flags32 + (static_cast<size_t>(frame) * pillars + p0) / 4;
-    const unsigned mine = __ldcg(fw) & (0x01010101u << q);     // bit q of each byte: this quarter still holds data there
-    float* row = accum + (static_cast<size_t>(frame) * pillars + p0) * C + q * 16;      // pillar rows are 64 floats apart
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 v[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (mine & (0xffu << (8 * i))) {
-            ldcg_256(row + i * C, v[i][0], v[i][1]);
-            ldcg_256(row + i * C + 8, v[i][2], v[i][3]);
-        } else {
-            v[i][0] = v[i][1] = v[i][2] = v[i][3] = z4;
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (mine & (0xffu << (8 * i))) {
-            st_zero_256(row + i * C);
-            st_zero_256(row + i * C + 8);
-        }
-    }
-    if (mine) atomicAnd(fw, ~mine);
-    float* dst = bev + (static_cast<size_t>(frame) * C + q * 16) * pillars + p0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float* d = dst + static_cast<size_t>(4 * k) * pillars;
-        __stcs(reinterpret_cast<float4*>(d), make_float4(v[0][k].x, v[1][k].x, v[2][k].x, v[3][k].x));
-        __stcs(reinterpret_cast<float4*>(d + pillars), make_float4(v[0][k].y, v[1][k].y, v[2][k].y, v[3][k].y));
-        __stcs(reinterpret_cast<float4*>(d + 2 * pillars), make_float4(v[0][k].z, v[1][k].z, v[2][k].z, v[3][k].z));
-        __stcs(reinterpret_cast<float4*>(d + 3 * pillars), make_float4(v[0][k].w, v[1][k].w, v[2][k].w, v[3][k].w));
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Layout pass built on the copy engine.  A CTA takes FT_P consecutive pillars of one frame:
 //   1. one thread per pillar reads the pillar's touched byte and, if set, fetches the pillar's 256-byte accumulator row with
@@ -200,189 +142,6 @@ finalize_tma_kernel(const __grid_constant__ CUtensorMap bev_map, float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Streaming layout pass: persistent CTAs walk the (frame, 64-pillar) tiles with a three-deep software pipeline in registers:
-//   touched bytes of tile i+2  ->  accumulator rows of tile i+1 (only where touched; 32-byte loads, lane = pillar, warp =
-//   channel octet)  ->  tile i: 16 conflict-free STS.32 per thread build the (channel, pillar) block in shared memory (bank =
-//   lane), the rows just read are re-zeroed with 32-byte stores, and ONE tiled TMA store writes the (64 x 64) block into the
-//   NCHW output.  The output block is double buffered: the copy engine drains tile i-1 while tile i is assembled, and a CTA
-//   never waits for DRAM latency in its loop because every load was issued one iteration earlier.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int FS_P = 64;
-constexpr int FS_THREADS = 256;
-
-__global__ void __launch_bounds__(FS_THREADS)
-finalize_stream_kernel(const __grid_constant__ CUtensorMap bev_map, float* __restrict__ accum, unsigned char* __restrict__ touched,
-                       long long pillars, int tiles_per_frame, int n_tiles, int frame_out0) {
-    constexpr int C = 64;
-    __shared__ __align__(128) float s_out[2][C * FS_P];          // [channel][pillar], TMA store source
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;   // w: channels 8w .. 8w+7
-    if (tid == 0) tma_prefetch_desc(&bev_map);
-
-    // pillar index (frame * pillars + p) of this lane's two pillars of tile t, or -1 past the end of the frame / the tiles
-    auto pillar_of_tile = [&](int t, int g) -> long long {
-        if (t >= n_tiles) return -1;
-        const int frame = t / tiles_per_frame;
-        const long long p = static_cast<long long>(t - frame * tiles_per_frame) * FS_P + g * 32 + lane;
-        return p < pillars ? static_cast<long long>(frame) * pillars + p : -1;
-    };
-    auto load_flags = [&](int t) -> unsigned {
-        unsigned f = 0;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            const long long gp = pillar_of_tile(t, g);
-            if (gp >= 0) f |= static_cast<unsigned>(__ldcg(touched + gp)) << (8 * g);
-        }
-        return f;
-    };
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto load_rows = [&](int t, unsigned f, float4 (&v)[2][2]) {
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            if (f & (0xffu << (8 * g))) ldcg_256(accum + pillar_of_tile(t, g) * C + w * 8, v[g][0], v[g][1]);
-            else v[g][0] = v[g][1] = z4;
-        }
-    };
-
-    auto emit_tile = [&](int t, int buf, unsigned f, const float4 (&v)[2][2]) {
-        float* dst = s_out[buf] + (w * 8) * FS_P + lane;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-            dst[g * 32 + 0 * FS_P] = v[g][0].x; dst[g * 32 + 1 * FS_P] = v[g][0].y;
-            dst[g * 32 + 2 * FS_P] = v[g][0].z; dst[g * 32 + 3 * FS_P] = v[g][0].w;
-            dst[g * 32 + 4 * FS_P] = v[g][1].x; dst[g * 32 + 5 * FS_P] = v[g][1].y;
-            dst[g * 32 + 6 * FS_P] = v[g][1].z; dst[g * 32 + 7 * FS_P] = v[g][1].w;
-            if (f & (0xffu << (8 * g))) {                         // restore the all-zero scratch
-                const long long gp = pillar_of_tile(t, g);
-                st_zero_256(accum + gp * C + w * 8);
-                if (w == 0) touched[gp] = 0;
-            }
-        }
-        fence_proxy_async();                                      // my STS -> visible to the copy engine
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // tile t-1 has left the other buffer
-        __syncthreads();
-        if (tid == 0) {
-            const int frame = t / tiles_per_frame;
-            tma_store_3d(&bev_map, s_out[buf], (t - frame * tiles_per_frame) * FS_P, 0, frame_out0 + frame);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-    };
-
-    // The pipeline registers rotate with period 3 (flags) and 2 (rows): six tiles per trip keep every index a compile-time
-    // constant, so nothing in flight is ever copied (a register move would wait for the load).
-    const int step = gridDim.x;
-    int t = blockIdx.x;
-    unsigned fl[3];
-    float4 rows[2][2][2];
-    fl[0] = load_flags(t);
-    fl[1] = load_flags(t + step);
-    load_rows(t, fl[0], rows[0]);
-    bool more = t < n_tiles;
-#pragma unroll 1
-    while (more) {
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            if (more) {
-                fl[(u + 2) % 3] = load_flags(t + 2 * step);                   // consumed two tiles from now
-                load_rows(t + step, fl[(u + 1) % 3], rows[(u + 1) % 2]);      // consumed by the next tile
-                emit_tile(t, u & 1, fl[u % 3], rows[u % 2]);
-                t += step;
-                more = t < n_tiles;
-            }
-        }
-    }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Wide streaming layout pass: like finalize_stream_kernel, but a tile is 256 consecutive pillars x ONE QUARTER of the channels,
-// so the TMA store writes 16 channel rows of 1 KB each (instead of 64 rows of 256 B): four times longer DRAM bursts for
-// the 10 MB/frame the pass has to write.  thread = pillar, 64-byte row quarter (two 32-byte loads, only where touched), 16
-// conflict-free STS.32 (bank = lane).  The touched bytes are read-only here (four quarter tiles share them); the launcher
-// clears the map afterwards with a memset node.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int FW_P = 256;
-constexpr int FW_C = 16;
-constexpr int FW_THREADS = 256;
-
-__global__ void __launch_bounds__(FW_THREADS)
-finalize_wide_kernel(const __grid_constant__ CUtensorMap bev_map, float* __restrict__ accum, const unsigned char* __restrict__ touched,
-                     long long pillars, int blocks_per_frame, int n_tiles, int frame_out0) {
-    constexpr int C = 64;
-    __shared__ __align__(128) float s_out[2][FW_C * FW_P];        // [channel][pillar], TMA store source
-    const int tid = threadIdx.x;
-    if (tid == 0) tma_prefetch_desc(&bev_map);
-
-    // tile t = (frame, pillar block, quarter), quarter fastest: the four quarters of a block run back to back on neighbouring
-    // CTAs, so the 256-byte rows are fetched from DRAM once
-    auto row_of_tile = [&](int t) -> long long {                  // element offset of this thread's 64 bytes, or -1
-        if (t >= n_tiles) return -1;
-        const int q = t & 3, b = t >> 2;
-        const int frame = b / blocks_per_frame;
-        const long long p = static_cast<long long>(b - frame * blocks_per_frame) * FW_P + tid;
-        return p < pillars ? (static_cast<long long>(frame) * pillars + p) * C + q * FW_C : -1;
-    };
-    auto load_flag = [&](int t) -> unsigned {
-        const long long r = row_of_tile(t);
-        return r >= 0 ? static_cast<unsigned>(__ldcg(touched + r / C)) : 0u;
-    };
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto load_row = [&](int t, unsigned f, float4 (&v)[4]) {
-        if (f) {
-            const float* src = accum + row_of_tile(t);
-            ldcg_256(src, v[0], v[1]);
-            ldcg_256(src + 8, v[2], v[3]);
-        } else {
-            v[0] = v[1] = v[2] = v[3] = z4;
-        }
-    };
-    auto emit_tile = [&](int t, int buf, unsigned f, const float4 (&v)[4]) {
-        float* dst = s_out[buf] + tid;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            dst[(4 * k + 0) * FW_P] = v[k].x; dst[(4 * k + 1) * FW_P] = v[k].y;
-            dst[(4 * k + 2) * FW_P] = v[k].z; dst[(4 * k + 3) * FW_P] = v[k].w;
-        }
-        if (f) {                                                  // restore the all-zero scratch
-            float* row = accum + row_of_tile(t);
-            st_zero_256(row);
-            st_zero_256(row + 8);
-        }
-        fence_proxy_async();
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // tile t-1 has left the other buffer
-        __syncthreads();
-        if (tid == 0) {
-            const int q = t & 3, b = t >> 2;
-            const int frame = b / blocks_per_frame;
-            tma_store_3d(&bev_map, s_out[buf], (b - frame * blocks_per_frame) * FW_P, q * FW_C, frame_out0 + frame);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-    };
-
-    const int step = gridDim.x;
-    int t = blockIdx.x;
-    unsigned fl[3];
-    float4 rows[2][4];
-    fl[0] = load_flag(t);
-    fl[1] = load_flag(t + step);
-    load_row(t, fl[0], rows[0]);
-    bool more = t < n_tiles;
-#pragma unroll 1
-    while (more) {
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-            if (more) {
-                fl[(u + 2) % 3] = load_flag(t + 2 * step);
-                load_row(t + step, fl[(u + 1) % 3], rows[(u + 1) % 2]);
-                emit_tile(t, u & 1, fl[u % 3], rows[u % 2]);
-                t += step;
-                more = t < n_tiles;
-            }
-        }
-    }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
 // Integer index dump (fiery.py:236-256) for parity checks; one thread per (frame, camera, depth, row, column) point.
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void point_indices_kernel(const LiftParams P, int64_t* __restrict__ idx_out, uint8_t* __restrict__ valid_out,
@@ -438,7 +197,7 @@ int lift_chunk_frames(int n_frames, long long pillars, int channels) {
 }
 
 int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stream);
-int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels, int n_frames, int box_pillars, int box_channels);
+int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels, int n_frames, int box_pillars);
 
 // Side streams of the forward chains, created once per device (non-blocking).  Concurrent callers may share them: every call
 // orders its work with its own events, so sharing only serialises.
@@ -455,6 +214,31 @@ static int side_streams(int n, cudaStream_t* out) {
     return FIERY_OK;
 }
 
+// NCHW output: the frames of a chunk are cut into groups, each a (tile kernel -> layout pass) chain on its own stream.  The
+// layout pass of one group (DRAM-bound) runs under the tile kernels of the others (issue-bound); only the last pass is
+// exposed.  Measured on B200 (profiles/r01_notes.md), 8 frames: 1 chain 84.7 us, 2 chains 78.3 us, 4 chains 73.3 us; 8 chains of
+// one frame (90 tiles) each fall back to 79.6 us, so a group keeps at least one tile per SM (148).  The same split of the
+// backward (re-layout -> tile kernel) gained nothing (159.2 -> 158.3 us) and is not done.
+static int g_max_chains = MAX_CHAINS;      // FIERY_CHAINS (A/B builds)
+static int g_chain_min_tiles = 148;        // FIERY_CHAIN_MIN_TILES (A/B builds)
+int lift_forward_groups(const LiftParams& P, int frames_in_chunk) {
+    int groups = frames_in_chunk < g_max_chains ? frames_in_chunk : g_max_chains;
+    const long long tiles_per_frame = static_cast<long long>(P.n_cameras) * P.n_wtiles;
+    while (groups > 1 && (frames_in_chunk / groups) * tiles_per_frame < g_chain_min_tiles) --groups;
+    return groups < 1 ? 1 : groups;
+}
+
+// kernel launches of one forward call (include/fiery_b200.h: fiery_lift_forward_launches)
+int lift_forward_launches(const LiftParams& P) {
+    if (P.n_frames <= 0) return 0;
+    if (P.bev_layout == FIERY_BEV_NHWC) return 1;
+    const int chunk = lift_chunk_frames(P.n_frames, P.pillars, P.C);
+    int n = 0;
+    for (int f0 = 0; f0 < P.n_frames; f0 += chunk)
+        n += 2 * lift_forward_groups(P, (P.n_frames - f0 < chunk) ? P.n_frames - f0 : chunk);
+    return n;
+}
+
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch,
                         cudaStream_t stream) {
     FIERY_REQUIRE(head_dtype == FIERY_DTYPE_F32, "head dtype %d not supported by this build (fp32 only)", head_dtype);
@@ -469,48 +253,27 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
         Q.frame0 = 0;
         return launch_forward_cols(Q, head, stream);
     }
-    // NCHW: lift into the channel-last accumulator, then the layout pass; chunked only to bound the scratch footprint.
-    // Within a chunk the frames are cut into up to `chains` groups, each a (tile kernel -> layout pass) chain on its own
-    // stream: the layout pass of one group (DRAM-bound) then runs under the tile kernel of the next (issue-bound), and only
-    // the last group's pass is exposed.  Frames are independent and every group owns its slice of the scratch, so the chains
-    // share nothing; they are forked from and joined back into the caller's stream with events (capturable in a CUDA graph).
+#ifdef FIERY_COLS_AB
+    if (const char* e = getenv("FIERY_CHAINS")) g_max_chains = atoi(e) < MAX_CHAINS ? atoi(e) : MAX_CHAINS;
+    if (const char* e = getenv("FIERY_CHAIN_MIN_TILES")) g_chain_min_tiles = atoi(e);
+#endif
+    // NCHW: lift into the channel-last accumulator, then the layout pass; chunked only to bound the scratch footprint
     const int chunk = lift_chunk_frames(P.n_frames, P.pillars, P.C);
     float* accum = scratch;                        // [accumulator floats of one chunk][one "touched" byte per pillar]
     unsigned char* touched = reinterpret_cast<unsigned char*>(scratch + static_cast<size_t>(chunk) * P.pillars * P.C);
-    const int bpf = static_cast<int>((P.pillars + FIN_THREADS - 1) / FIN_THREADS);
-    // 3 streaming pass (TMA store), 2 bulk-copy pass, 1 register-transposing pass, 0 one thread per pillar
-    int pass = P.pillars % 4 == 0 ? 3 : 0;
-    int ctas_per_sm = 6;
-    int chains = 2;
-    int min_tiles_per_sm = 2;
-#ifdef FIERY_COLS_AB
-    if (const char* e = getenv("FIERY_FINALIZE")) pass = P.pillars % 4 == 0 ? atoi(e) : 0;
-    if (const char* e = getenv("FIERY_FINALIZE_CTAS")) ctas_per_sm = atoi(e);
-    if (const char* e = getenv("FIERY_CHAINS")) chains = atoi(e);
-    if (const char* e = getenv("FIERY_CHAIN_MIN_TILES")) min_tiles_per_sm = atoi(e);
-#endif
-    if (chains > MAX_CHAINS) chains = MAX_CHAINS;
+    const bool tma_pass = P.pillars % 4 == 0;      // the output map needs a 16-byte row pitch
     CUtensorMap bev_map;
-    if (pass >= 2) {
-        rc = pass == 4 ? encode_bev_map(&bev_map, bev_out, P.pillars, P.C, P.n_frames, FW_P, FW_C)
-                       : encode_bev_map(&bev_map, bev_out, P.pillars, P.C, P.n_frames, FT_P, P.C);
+    if (tma_pass) {
+        rc = encode_bev_map(&bev_map, bev_out, P.pillars, P.C, P.n_frames, FT_P);
         if (rc != FIERY_OK) return rc;
-    }
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0;
-        FIERY_CUDA_CHECK(cudaGetDevice(&dev));
-        FIERY_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     for (int f0 = 0; f0 < P.n_frames; f0 += chunk) {
         const int nf = (P.n_frames - f0 < chunk) ? P.n_frames - f0 : chunk;
-        // a group should fill the machine at least once with tiles (2 per SM), or the split only adds launches
-        int groups = chains;
-        while (groups > 1 && static_cast<long long>(nf / groups) * P.n_cameras * P.n_wtiles < static_cast<long long>(min_tiles_per_sm) * n_sm) --groups;
-        cudaStream_t side[MAX_CHAINS] = {stream};
+        const int groups = lift_forward_groups(P, nf);
+        cudaStream_t chain[MAX_CHAINS] = {stream};
         cudaEvent_t fork = nullptr;
-        if (groups > 1) {
-            rc = side_streams(groups - 1, side + 1);
+        if (groups > 1) {                           // fork: the side streams start behind everything queued on the caller's
+            rc = side_streams(groups - 1, chain + 1);
             if (rc != FIERY_OK) return rc;
             FIERY_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
             FIERY_CUDA_CHECK(cudaEventRecord(fork, stream));
@@ -518,44 +281,25 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
         for (int g = 0; g < groups; ++g) {
             const int s0 = static_cast<int>(static_cast<long long>(nf) * g / groups);
             const int s1 = static_cast<int>(static_cast<long long>(nf) * (g + 1) / groups);
-            cudaStream_t st = side[g];
+            cudaStream_t st = chain[g];
             if (g > 0) FIERY_CUDA_CHECK(cudaStreamWaitEvent(st, fork, 0));
             Q.frame0 = f0 + s0;
             Q.n_frames = s1 - s0;
             Q.accum = accum + static_cast<size_t>(s0) * P.pillars * P.C;
             Q.touched = touched + static_cast<size_t>(s0) * P.pillars;
-            float* out_g = bev_out + static_cast<size_t>(Q.frame0) * P.C * P.pillars;
             rc = launch_forward_cols(Q, head, st);
             if (rc != FIERY_OK) return rc;
-            if (pass == 4) {
-                const int bpf256 = static_cast<int>((P.pillars + FW_P - 1) / FW_P);
-                const long long n_tiles = 4ll * bpf256 * Q.n_frames;
-                FIERY_REQUIRE(n_tiles < (1ll << 30), "layout pass: too many tiles");
-                const long long cap = static_cast<long long>(n_sm) * ctas_per_sm;
-                finalize_wide_kernel<<<static_cast<unsigned>(n_tiles < cap ? n_tiles : cap), FW_THREADS, 0, st>>>(
-                    bev_map, Q.accum, Q.touched, P.pillars, bpf256, static_cast<int>(n_tiles), Q.frame0);
-                FIERY_CUDA_CHECK(cudaMemsetAsync(Q.touched, 0, static_cast<size_t>(Q.n_frames) * P.pillars, st));
-            } else if (pass == 3) {
-                const int tpf = static_cast<int>((P.pillars + FS_P - 1) / FS_P);
-                const long long n_tiles = static_cast<long long>(tpf) * Q.n_frames;
-                FIERY_REQUIRE(n_tiles < (1ll << 30), "layout pass: too many tiles");
-                const long long cap = static_cast<long long>(n_sm) * ctas_per_sm;
-                finalize_stream_kernel<<<static_cast<unsigned>(n_tiles < cap ? n_tiles : cap), FS_THREADS, 0, st>>>(
-                    bev_map, Q.accum, Q.touched, P.pillars, tpf, static_cast<int>(n_tiles), Q.frame0);
-            } else if (pass == 2) {
+            if (tma_pass) {
                 const int tpf = static_cast<int>((P.pillars + FT_P - 1) / FT_P);
                 finalize_tma_kernel<<<static_cast<unsigned>(tpf) * Q.n_frames, FT_THREADS, 0, st>>>(bev_map, Q.accum, Q.touched,
                                                                                                  P.pillars, tpf, Q.frame0);
-            } else if (pass == 1) {
-                const int bpf4 = static_cast<int>((P.pillars / 4 + FIN_THREADS - 1) / FIN_THREADS);
-                finalize_clear_nchw_kernel<<<static_cast<unsigned>(bpf4) * Q.n_frames * 4, FIN_THREADS, 0, st>>>(
-                    Q.accum, reinterpret_cast<unsigned*>(Q.touched), out_g, P.pillars, bpf4);
             } else {
-                finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * Q.n_frames, FIN_THREADS, 0, st>>>(Q.accum, Q.touched, out_g,
-                                                                                                    P.pillars, bpf);
+                const int bpf = static_cast<int>((P.pillars + FIN_THREADS - 1) / FIN_THREADS);
+                finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * Q.n_frames, FIN_THREADS, 0, st>>>(
+                    Q.accum, Q.touched, bev_out + static_cast<size_t>(Q.frame0) * P.C * P.pillars, P.pillars, bpf);
             }
             FIERY_CUDA_CHECK(cudaGetLastError());
-            if (g > 0) {                                            // join the chain back into the caller's stream
+            if (g > 0) {                            // join the chain back into the caller's stream
                 cudaEvent_t done;
                 FIERY_CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
                 FIERY_CUDA_CHECK(cudaEventRecord(done, st));

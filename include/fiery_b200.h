@@ -103,6 +103,11 @@ FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head
                        const float* frustum_u, const float* frustum_v, const float* frustum_d,
                        float* bev_out, float* scratch, void* stream);
 
+/* Number of kernel launches one fiery_lift_forward call with this descriptor issues (NHWC: the tile kernel; NCHW: tile kernel
+ * + layout pass per frame group; groups of frames run as concurrent chains on internal streams that are forked from and
+ * joined back into `stream` with events, so the call behaves like work queued on `stream` and can be captured in a graph). */
+FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* desc);
+
 /* Bytes of device workspace fiery_lift_backward needs when grad_bev is FIERY_BEV_NCHW (it is re-laid out channel-last
  * there); 0 for NHWC.  Contents on entry/exit are irrelevant. */
 FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* desc);

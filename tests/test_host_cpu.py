@@ -49,6 +49,23 @@ def test_argument_validation_without_gpu():
     assert lib.fiery_voxels_summing_plan(0, None, None, ctypes.byref(n), None) == 0 and n.value == 0
 
 
+def test_forward_launch_plan_without_gpu():
+    """fiery_lift_forward_launches is host logic: one tile kernel for channel-last output; for NCHW one (tile kernel, layout
+    pass) chain per frame group, a group holding at least one tile per SM (148) and at most four groups per call."""
+    lib = _lib.load()
+    d = _lib.LiftDesc()
+    d.n_cameras, d.depth_bins, d.channels, d.feat_h, d.feat_w = 6, 48, 64, 28, 60        # 90 tiles per frame
+    d.bev_x, d.bev_y, d.bev_z = 200, 200, 1
+    d.bev_layout = _lib.BEV_NCHW
+    expect = {0: 0, 1: 2, 2: 2, 3: 2, 4: 4, 5: 4, 6: 6, 8: 8, 9: 8, 12: 8, 100: 8}
+    for frames, launches in expect.items():
+        d.n_frames = frames
+        assert lib.fiery_lift_forward_launches(d) == launches, frames
+    d.n_frames, d.bev_layout = 8, _lib.BEV_NHWC
+    assert lib.fiery_lift_forward_launches(d) == 1
+    assert lib.fiery_lift_forward_launches(None) == 0
+
+
 def test_no_cpu_fallback():
     """The product path refuses CPU tensors instead of silently computing on the host."""
     m = LiftSplat.from_config(CONFIGS["cfg1_tiny"])

@@ -226,6 +226,42 @@ def test_graph_capture_and_host_pipeline_match_eager():
     assert O.normwise_error(out1, out) < 1e-6
 
 
+def test_frame_groups_match_frame_by_frame_calls():
+    """A batch large enough to be cut into frame groups (tile kernel -> layout pass chains on forked streams,
+    lift_fwd.cu:lift_forward_groups) returns, frame for frame, what single-frame calls return, leaves the scratch all-zero,
+    and reports its launches through fiery_lift_forward_launches."""
+    from fiery_b200 import _lib
+    from fiery_b200.geometry import _stream_ptr
+    cfg = LiftConfig(**{**CONFIGS["cfg2_static_lss"].__dict__, "frames": 9})
+    dev = _dev()
+    K, E = make_calibration(cfg, seed=31)
+    Kd, Ed = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
+    hd = torch.from_numpy(make_head(cfg, seed=31)).to(dev)
+    lift = LiftSplat.from_config(cfg).to(dev)
+    lib = _lib.load()
+    c = lift._constants(dev)
+    desc = lift._desc(c, cfg.frames, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, _lib.BEV_NCHW)
+    n_launch = int(lib.fiery_lift_forward_launches(desc))
+    assert n_launch >= 4 and n_launch % 2 == 0          # more than one (tile kernel, layout pass) chain
+    scratch = torch.zeros(int(lib.fiery_lift_scratch_bytes(desc)) // 4, dtype=torch.float32, device=dev)
+    X, Y = cfg.bev_hw
+    out = torch.full((cfg.frames, cfg.out_channels, X, Y), float("nan"), dtype=torch.float32, device=dev)
+    for _ in range(2):                                   # second call: the scratch left by the first must be clean
+        _lib.check(lib.fiery_lift_forward(desc, hd.data_ptr(), Kd.data_ptr(), Ed.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
+                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), _stream_ptr(dev)), "fwd")
+    torch.cuda.synchronize()
+    assert bool((scratch == 0).all())
+    n = cfg.n_cameras
+    with torch.no_grad():
+        for f in range(cfg.frames):
+            one = lift(hd[f * n:(f + 1) * n], Kd[f:f + 1], Ed[f:f + 1])
+            assert O.normwise_error(out[f:f + 1].cpu(), one.cpu()) < 1e-6, f"frame {f}"
+    d1 = lift._desc(c, 1, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, _lib.BEV_NCHW)
+    assert int(lib.fiery_lift_forward_launches(d1)) == 2
+    d1.bev_layout = _lib.BEV_NHWC
+    assert int(lib.fiery_lift_forward_launches(d1)) == 1
+
+
 def test_row_order_of_the_frustum_is_not_assumed():
     """The kernels pool along image columns but evaluate the geometry of every row: nothing may rely on the frustum's row
     coordinates being sorted (fiery.py:122 makes them a linspace).  A frustum with permuted rows must give the lift of

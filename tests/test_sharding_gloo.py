@@ -55,7 +55,8 @@ def _worker(rank, world, port, frames, out_q):
         dist.all_gather(gathered, bev.detach())
     dist.barrier()
     if rank == 0:
-        out_q.put((grad, torch.cat(gathered) if gathered is not None else None))
+        # numpy arrays travel by value; torch tensors would be shared through the producer's fd server, which dies with it
+        out_q.put((grad.numpy(), torch.cat(gathered).numpy() if gathered is not None else None))
     dist.destroy_process_group()
 
 
@@ -69,6 +70,7 @@ def test_two_rank_sharding_matches_single_process():
     for p in procs:
         p.start()
     grad, bev = q.get(timeout=240)
+    grad, bev = torch.from_numpy(grad), torch.from_numpy(bev)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0

@@ -71,46 +71,53 @@ best = min((v for v in res["tile"] if "us_mean" in res["tile"][v] and res["tile"
 res["best_tile"] = best
 out_nchw = torch.empty((F, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
 ref_nchw = ref.permute(0, 3, 1, 2)
-combos = os.environ.get("AB_COMBOS", "-1:2:6:1 -1:2:6:2 -1:3:4:1 -1:3:4:2 -1:4:4:1 -1:4:4:2 -1:4:6:2 -1:4:4:4 -1:2:6:4").split()
+combos = os.environ.get("AB_COMBOS", "1:148 2:148 4:148 8:148 8:90 4:296 8:296").split()
+from fiery_b200.synthetic import make_grad_bev
+gout = torch.from_numpy(make_grad_bev(cfg, seed=100)).to(dev)
 for combo in combos:
-    v, fin, ctas, chains = (int(x) for x in combo.split(":"))
-    os.environ["FIERY_COLS_VARIANT"] = str(v)
-    os.environ["FIERY_FINALIZE"] = str(fin)
-    os.environ["FIERY_FINALIZE_CTAS"] = str(ctas)
+    chains, min_tiles = (int(x) for x in combo.split(":"))
+    os.environ["FIERY_COLS_VARIANT"] = "-1"
     os.environ["FIERY_CHAINS"] = str(chains)
-    os.environ["FIERY_CHAIN_MIN_TILES"] = "1" if chains > 2 else "2"
-    if True:
-        run, desc = runner(_lib.BEV_NCHW, out_nchw, None)
-        scratch = torch.zeros(int(lib.fiery_lift_scratch_bytes(desc)) // 4, dtype=torch.float32, device=dev)
-        run, desc = runner(_lib.BEV_NCHW, out_nchw, scratch)
-        out_nchw.fill_(float("nan"))
-        run(); torch.cuda.synchronize()
-        err = float((out_nchw - ref_nchw).norm() / ref_nchw.norm())
-        clean = bool((scratch == 0).all().item())
-        for _ in range(3):
-            run()
-        mean, mn = timed(run)
-        # CUDA-graph replay of the same launches
-        g = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            sp = s.cuda_stream
-            def run_s():
-                _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
-                                                  c["d"].data_ptr(), out_nchw.data_ptr(), scratch.data_ptr(), sp), "fwd")
-            run_s(); torch.cuda.synchronize()
-            with torch.cuda.graph(g, stream=s):
-                run_s()
-        torch.cuda.current_stream().wait_stream(s)
-        out_nchw.fill_(float("nan"))
-        gmean, gmn = timed(g.replay)
-        torch.cuda.synchronize()
-        err2 = float((out_nchw - ref_nchw).norm() / ref_nchw.norm())
-        clean2 = bool((scratch == 0).all().item())
-        res["layout_pass"][combo] = {"us_mean": mean, "us_min": mn, "graph_us_mean": gmean, "graph_us_min": gmn,
-                                     "rel_err": max(err, err2), "scratch_clean": clean and clean2}
-        print("pass tile:fin:ctas:chains", combo, res["layout_pass"][combo], flush=True)
+    os.environ["FIERY_CHAIN_MIN_TILES"] = str(min_tiles)
+    run, desc = runner(_lib.BEV_NCHW, out_nchw, None)
+    scratch = torch.zeros(int(lib.fiery_lift_scratch_bytes(desc)) // 4, dtype=torch.float32, device=dev)
+    run, desc = runner(_lib.BEV_NCHW, out_nchw, scratch)
+    out_nchw.fill_(float("nan"))
+    run(); torch.cuda.synchronize()
+    err = float((out_nchw - ref_nchw).norm() / ref_nchw.norm())
+    clean = bool((scratch == 0).all().item())
+    for _ in range(3):
+        run()
+    mean, mn = timed(run)
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        sp = s.cuda_stream
+        def run_s():
+            _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
+                                              c["d"].data_ptr(), out_nchw.data_ptr(), scratch.data_ptr(), sp), "fwd")
+        run_s(); torch.cuda.synchronize()
+        with torch.cuda.graph(g, stream=s):
+            run_s()
+    torch.cuda.current_stream().wait_stream(s)
+    out_nchw.fill_(float("nan"))
+    gmean, gmn = timed(g.replay)
+    torch.cuda.synchronize()
+    err2 = float((out_nchw - ref_nchw).norm() / ref_nchw.norm())
+    clean2 = bool((scratch == 0).all().item())
+    # backward (eager, through the host layer: workspace allocation + re-layout + tile kernel)
+    gh = lift._launch_backward(head, K_d, E_d, gout)
+    if combo == combos[0]:
+        gh_ref = gh.clone()
+    berr = float((gh - gh_ref).norm() / gh_ref.norm())
+    for _ in range(3):
+        lift._launch_backward(head, K_d, E_d, gout)
+    bmean, bmn = timed(lambda: lift._launch_backward(head, K_d, E_d, gout))
+    res["layout_pass"][combo] = {"us_mean": mean, "graph_us_mean": gmean, "graph_us_min": gmn, "rel_err": max(err, err2),
+                                 "scratch_clean": clean and clean2, "launches": int(lib.fiery_lift_forward_launches(desc)),
+                                 "bwd_us_mean": bmean, "bwd_rel_err_vs_first": berr}
+    print("chains:min_tiles", combo, res["layout_pass"][combo], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", f"ab_{wl}.json"), "w") as fh:
     json.dump(res, fh, indent=1)

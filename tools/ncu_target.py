@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Small ncu target: runs only the launches to be captured, through the C ABI.
+    python tools/ncu_target.py <workload> tile    # the column tile kernel alone (channel-last target), whole batch, 4 launches
+    python tools/ncu_target.py <workload> step    # the NCHW step (tile kernels + layout passes of every frame group), 4 calls
+    python tools/ncu_target.py <workload> bwd     # NCHW backward (re-layout + backward tile kernel), 3 calls
+"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from fiery_b200 import _lib
+from fiery_b200.geometry import _stream_ptr
+from fiery_b200.lift import LiftSplat
+from fiery_b200.synthetic import CONFIGS, make_calibration, make_grad_bev, make_head
+
+wl, mode = sys.argv[1], sys.argv[2]
+cfg = CONFIGS[wl]
+dev = torch.device("cuda:0")
+lib = _lib.load()
+K, E = make_calibration(cfg, seed=100)
+head = torch.from_numpy(make_head(cfg, seed=100)).to(dev)
+K_d, E_d = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
+lift = LiftSplat.from_config(cfg).to(dev)
+c = lift._constants(dev)
+X, Y = cfg.bev_hw
+if mode == "bwd":
+    g = torch.from_numpy(make_grad_bev(cfg, seed=100)).to(dev)
+    for _ in range(3):
+        lift._launch_backward(head, K_d, E_d, g)
+else:
+    layout = _lib.BEV_NHWC if mode == "tile" else _lib.BEV_NCHW
+    desc = lift._desc(c, cfg.frames, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, layout)
+    out = torch.zeros((cfg.frames, X, Y, cfg.out_channels) if mode == "tile" else (cfg.frames, cfg.out_channels, X, Y), device=dev)
+    scratch = torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
+    for _ in range(4):
+        _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
+                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), _stream_ptr(dev)), "fwd")
+torch.cuda.synchronize()
