@@ -118,17 +118,24 @@ finalize_tma_kernel(const __grid_constant__ CUtensorMap bev_map, float* __restri
     __syncthreads();                                    // s_flag
     mbar_wait(&bar, 0);                                 // every fetched row has landed
     {
+        // 16-byte reads: a quarter-warp (8 lanes = 8 pillars, rows 256 B apart) reads the 8 different 16-byte chunks
+        // chunk0 + (i ^ (lane & 7)) of a 32-channel block, so every LDS.128 phase covers all 32 banks; the four values go to
+        // channel rows 4*chunk .. 4*chunk+3 of this lane's pillar column (bank = lane)
         const int lane = tid & 31, w = tid >> 5;
         const int pl = (w & 1) * 32 + lane;             // pillar of this lane
-        const int c_hi = (w >> 2) * 32;                 // 32-channel block; (w >> 1) & 1 picks its half
-        const int c_lo = ((w >> 1) & 1) * 16;
+        const int chunk0 = ((w >> 1) & 1) * 8;          // 32-channel block = 8 chunks of 4 channels
+        const int i0 = (w >> 2) * 4;                    // this warp's four of the eight rotations
         const bool have = s_flag[pl] != 0;
-        const float* src = s_in + pl * C + c_hi;
-        float* dst = s_out + c_hi * FT_P + pl;
+        const float4* src = reinterpret_cast<const float4*>(s_in + pl * C);
+        float* dst = s_out + pl;
+        const int l7 = lane & 7;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const int c = (c_lo + i) ^ lane;
-            dst[c * FT_P] = have ? src[c] : 0.f;
+        for (int ii = 0; ii < 4; ++ii) {
+            const int chunk = chunk0 + ((i0 + ii) ^ l7);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (have) v = src[chunk];
+            float* d = dst + chunk * (4 * FT_P);
+            d[0] = v.x; d[FT_P] = v.y; d[2 * FT_P] = v.z; d[3 * FT_P] = v.w;
         }
     }
     fence_proxy_async();                                // generic-proxy writes (s_out, s_zero) -> visible to the copy engine
@@ -217,8 +224,9 @@ static int side_streams(int n, cudaStream_t* out) {
 // NCHW output: the frames of a chunk are cut into groups, each a (tile kernel -> layout pass) chain on its own stream.  The
 // layout pass of one group (DRAM-bound) runs under the tile kernels of the others (issue-bound); only the last pass is
 // exposed.  Measured on B200 (profiles/r01_notes.md), 8 frames: 1 chain 84.7 us, 2 chains 78.3 us, 4 chains 73.3 us; 8 chains of
-// one frame (90 tiles) each fall back to 79.6 us, so a group keeps at least one tile per SM (148).  The same split of the
-// backward (re-layout -> tile kernel) gained nothing (159.2 -> 158.3 us) and is not done.
+// one frame (90 tiles) each fall back to 79.6 us, so a group keeps at least one tile per SM (148).  A shorter last group (its
+// pass is the exposed one) does not help (137 -> 141 us at 400x200), and the same split of the backward (re-layout -> tile
+// kernel) gained nothing (159.2 -> 158.3 us); neither is done.
 static int g_max_chains = MAX_CHAINS;      // FIERY_CHAINS (A/B builds)
 static int g_chain_min_tiles = 148;        // FIERY_CHAIN_MIN_TILES (A/B builds)
 int lift_forward_groups(const LiftParams& P, int frames_in_chunk) {

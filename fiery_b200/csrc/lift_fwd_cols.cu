@@ -242,7 +242,7 @@ __device__ __forceinline__ void flush_depth(unsigned long long (&acc)[CPL][DD][2
 
 // CPL channels per lane, DD depths per unit: a unit is 64 / CPL lanes, a tile 48 / DD units.
 //   CPL 2, DD 2: 768 threads (a unit is a warp)      CPL 2, DD 4: 384 threads      CPL 4, DD 4: 192 threads (a unit is a half-warp)
-template <int CPL, int DD, int MINB>
+template <int CPL, int DD, int MINB, int UNR = 2>
 __global__ void __launch_bounds__((COLS_DPAD / DD) * (64 / CPL), MINB)
 lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const LiftParams P) {
     constexpr int LPU = 64 / CPL;                     // lanes per unit
@@ -321,7 +321,7 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
     // different depths would otherwise diverge on every event).  All are fetched one row ahead: the chain load -> reduce ->
     // branch is long.
     unsigned own = 0, flush = 0, mw = 0;              // row 0 starts every run
-#pragma unroll 2
+#pragma unroll UNR
     for (int h = 0; h < hh; ++h, pp += COLS_DPAD * WT, cp += 64 * WT, plp += COLS_NPAIR, ++evp) {
         const unsigned ev_next = *evp;                                // the word after the last row stays 0
         if (mw) flush_depth<CPL, DD, 0>(acc, mw, own, flush, plp, out);
@@ -358,15 +358,15 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
 
 int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams& P, int channels_per_lane);
 
-template <int CPL, int DD, int MINB>
+template <int CPL, int DD, int MINB, int UNR = 2>
 static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStream_t stream) {
     constexpr int NU = COLS_DPAD / DD, NT = NU * (64 / CPL);
     const ColsLayout L(P.hh, P.C, NU);
     static bool configured = false;
     if (!configured) {
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // ask for the full shared-memory carve-out (3 x 74 KB per SM for the reference shape)
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
@@ -375,7 +375,7 @@ static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStre
     const int rc = encode_head_maps_cols(&maps, head, P, CPL);
     if (rc != FIERY_OK) return rc;
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
-    lift_forward_cols_kernel<CPL, DD, MINB><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
+    lift_forward_cols_kernel<CPL, DD, MINB, UNR><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }
@@ -388,7 +388,8 @@ int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stre
     FIERY_REQUIRE(P.C == 64 && P.D <= COLS_DPAD, "column kernel: C=%d D=%d not supported", P.C, P.D);
     // Unit shape, measured on B200 (profiles/r01_notes.md): DD = 3 (512 threads, 58 registers) is 7-8 % faster when the grid fills
     // whole waves of 2 tiles per SM (9 frames: 55.3 vs 60.2 us, 12 frames at 400x200: 72.0 vs 77.1 us); DD = 2 (768 threads) is
-    // faster while tiles run alone on an SM, i.e. when the last wave is at most half full (8 frames: 52.3 vs 53.4 us).
+    // faster while tiles run alone on an SM, i.e. when the last wave is at most half full (8 frames: 52.3 vs 53.4 us; its row
+    // loop is not unrolled: 51.1 vs 52.3 us with two rows per trip, 56.4 us with four -- 40 registers leave no room).
     int n_sm = 0, dev = 0;
     FIERY_CUDA_CHECK(cudaGetDevice(&dev));
     FIERY_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
@@ -404,11 +405,12 @@ int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stre
         case 5: return launch_forward_cols_t<4, 2, 3>(P, head, stream);
         case 6: return launch_forward_cols_t<4, 3, 3>(P, head, stream);
         case 7: return launch_forward_cols_t<2, 4, 3>(P, head, stream);
+        case 8: return launch_forward_cols_t<2, 2, 2, 2>(P, head, stream);
         default: break;
     }
 #endif
     if (variant == 2) return launch_forward_cols_t<2, 3, 2>(P, head, stream);
-    return launch_forward_cols_t<2, 2, 2>(P, head, stream);
+    return launch_forward_cols_t<2, 2, 2, 1>(P, head, stream);
 }
 
 }  // namespace fiery
