@@ -143,20 +143,42 @@ __global__ void vs_backward_kernel(int64_t n_rows, int C, const float* __restric
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
+// Scratch of the plan (per-tile run counts + the total), cached per host thread and device and grown on demand: the plan
+// synchronises its stream before it returns, so the buffer is idle between calls.  (A cudaMallocAsync/cudaFreeAsync pair per
+// call costs from 0.3 ms to over 100 ms when the default pool hands its memory back at every synchronise.)
+struct PlanScratch {
+    int* counts = nullptr;
+    size_t bytes = 0;
+    int64_t* pinned_total = nullptr;
+};
+
 int vs_plan(int64_t n_rows, const int64_t* ranks, int32_t* seg, int64_t* host_n, cudaStream_t stream) {
+    static thread_local PlanScratch scratch[16];
+    int dev = 0;
+    FIERY_CUDA_CHECK(cudaGetDevice(&dev));
+    FIERY_REQUIRE(dev >= 0 && dev < 16, "device %d out of range", dev);
+    PlanScratch& S = scratch[dev];
     const int n_tiles = static_cast<int>((n_rows + SCAN_TILE - 1) / SCAN_TILE);
-    int* tile_counts = nullptr;
-    int64_t* d_n = nullptr;
     const int padded = (n_tiles + 3) & ~3;                       // keeps the trailing int64 16-byte aligned
-    FIERY_CUDA_CHECK(cudaMallocAsync(&tile_counts, sizeof(int) * padded + sizeof(int64_t) * 2, stream));
-    d_n = reinterpret_cast<int64_t*>(tile_counts + padded);
+    const size_t need = sizeof(int) * padded + sizeof(int64_t) * 2;
+    if (S.bytes < need) {
+        if (S.counts) FIERY_CUDA_CHECK(cudaFree(S.counts));
+        S.counts = nullptr;
+        S.bytes = 0;
+        const size_t grow = need * 2 > (1u << 16) ? need * 2 : (1u << 16);
+        FIERY_CUDA_CHECK(cudaMalloc(&S.counts, grow));
+        S.bytes = grow;
+    }
+    if (!S.pinned_total) FIERY_CUDA_CHECK(cudaHostAlloc(&S.pinned_total, sizeof(int64_t), cudaHostAllocDefault));
+    int* tile_counts = S.counts;
+    int64_t* d_n = reinterpret_cast<int64_t*>(tile_counts + padded);
     vs_count_kernel<<<n_tiles, SCAN_THREADS, 0, stream>>>(n_rows, ranks, tile_counts);
     vs_scan_tiles_kernel<<<1, 1024, 0, stream>>>(n_tiles, tile_counts, n_rows, d_n);
     vs_assign_kernel<<<n_tiles, SCAN_THREADS, 0, stream>>>(n_rows, ranks, tile_counts, seg);
     FIERY_CUDA_CHECK(cudaGetLastError());
-    FIERY_CUDA_CHECK(cudaMemcpyAsync(host_n, d_n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
-    FIERY_CUDA_CHECK(cudaFreeAsync(tile_counts, stream));
+    FIERY_CUDA_CHECK(cudaMemcpyAsync(S.pinned_total, d_n, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
     FIERY_CUDA_CHECK(cudaStreamSynchronize(stream));   // U sizes the outputs (the reference syncs here too, geometry.py:295)
+    *host_n = *S.pinned_total;
     return FIERY_OK;
 }
 
