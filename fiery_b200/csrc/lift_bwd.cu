@@ -7,7 +7,7 @@
 //     g_ctx[p][c]  = sum_d prob[p][d] * G[pi(p,d)][c]
 //     g_prob[p][d] = sum_c ctx[p][c]  * G[pi(p,d)][c]
 //     g_logit[p][d] = prob[p][d] * (g_prob[p][d] - sum_d' prob[p][d'] g_prob[p][d'])          (softmax backward)
-// The tile staging (TMA, softmax, transposes, pillar ranks, change bits) is shared with the forward kernel.  A thread
+// The tile staging (TMA, softmax, transposes, pillar ranks, change bits) lives in lift_tile.cuh.  A thread
 // owns one column, a group of <= MAXR consecutive rows and 4 channels; it loops over the depth blocks keeping the
 // 8 x 4 gradient values G of the current pillars in registers (reloaded from the channel-last grad_bev only where a
 // change bit says the pillar changed), so g_ctx needs no cross-thread reduction; g_prob is reduced over the 16 channel
@@ -277,7 +277,10 @@ static int launch_backward_t(const HeadMaps& hm, const HeadMaps& gm, const LiftP
     FIERY_REQUIRE((P.hh + DBLKS - 1) / DBLKS <= MAXR && P.hh <= 32, "feature map too tall for this build: h=%d", P.hh);
     const int smem = L.total + L.PX * TileLayout<DBLKS>::DPAD * 4;
     FIERY_REQUIRE(smem <= 227 * 1024, "tile needs %d bytes of shared memory", smem);
-    static int smem_configured = 0;
+    static int smem_configured_on[64] = {};           // function attributes are per device
+    int dev_id = 0;
+    FIERY_CUDA_CHECK(cudaGetDevice(&dev_id));
+    int& smem_configured = smem_configured_on[dev_id & 63];
     if (smem > smem_configured) {
         FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_backward_kernel<DBLKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         smem_configured = smem;

@@ -9,13 +9,12 @@
 namespace fiery {
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Finalize for NCHW output: accum (B', X*Y, C) -> bev (B', C, X*Y).  One thread per pillar: a lane reads its pillar's 256-byte
-// accumulator row as 16 independent 16-byte loads (its own two cache lines, so the sectors are fully used through L1),
-// and the warp then writes one channel of 32 consecutive pillars per store instruction -- a full 128-byte line.  No
-// shared-memory transpose (measured: the transposing variants are bound by 16-byte-per-lane scattered stores or by
-// bank conflicts, tools/microbench/finalize_variants.cu).  Only ~1/3-1/2 of the pillars receive any point, and the lift
-// kernel marks those in a byte map: unmarked pillars are written as zeros without touching the accumulator; marked
-// rows and their marks are re-zeroed on the way, which restores the scratch invariant of include/fiery_b200.h.
+// Fallback layout pass for NCHW output when X*Y is not a multiple of 4 (the TMA pass below needs a 16-byte row pitch):
+// accum (B', X*Y, C) -> bev (B', C, X*Y).  One thread per pillar: a lane reads its pillar's 256-byte accumulator row as 16
+// independent 16-byte loads (its own two cache lines, so the sectors are fully used through L1), and the warp then writes one
+// channel of 32 consecutive pillars per store instruction -- a full 128-byte line.  Only ~1/3-1/2 of the pillars receive any
+// point, and the tile kernel marks those in a byte map: unmarked pillars are written as zeros without touching the
+// accumulator; marked rows and their marks are re-zeroed on the way (scratch invariant of include/fiery_b200.h).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 256;
 __global__ void __launch_bounds__(FIN_THREADS)
@@ -53,8 +52,8 @@ finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flag
 //   1. one thread per pillar reads the pillar's touched byte and, if set, fetches the pillar's 256-byte accumulator row with
 //      a 1-D bulk copy (cp.async.bulk, completion on an mbarrier) -- only rows that received points are read, each as one
 //      contiguous 256-byte burst;
-//   2. the (pillar, channel) block is transposed shared -> shared with an XOR-swizzled lane mapping (reads hit bank
-//      (c ^ lane) mod 32, writes bank lane: both conflict free); rows that were not fetched read as zero;
+//   2. the (pillar, channel) block is transposed shared -> shared: 16-byte reads in an XOR-rotated chunk order (every
+//      quarter-warp phase covers all 32 banks), 4-byte writes with bank = lane; rows that were not fetched read as zero;
 //   3. one tiled TMA store writes the (64 channels x FT_P pillars) block into the NCHW output (256 contiguous bytes per
 //      channel row), and a 256-byte bulk copy of zeros per fetched row plus a byte store per mark restore the scratch
 //      invariant of include/fiery_b200.h.

@@ -362,7 +362,10 @@ template <int CPL, int DD, int MINB, int UNR = 2>
 static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStream_t stream) {
     constexpr int NU = COLS_DPAD / DD, NT = NU * (64 / CPL);
     const ColsLayout L(P.hh, P.C, NU);
-    static bool configured = false;
+    static bool configured_on[64] = {};              // function attributes are per device
+    int dev_id = 0;
+    FIERY_CUDA_CHECK(cudaGetDevice(&dev_id));
+    bool& configured = configured_on[dev_id & 63];
     if (!configured) {
         FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // ask for the full shared-memory carve-out (3 x 74 KB per SM for the reference shape)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an Nsight Compute report into text: key section metrics, DRAM traffic, and (for kernels built with
 -lineinfo) an instruction/stall breakdown per __syncthreads()-delimited phase.  Usage:
-    python tools/ncu_summary.py gpurun_out/prof_lift_fwd.ncu-rep > profiles/r01_lift_forward_kernel.txt
+    python tools/ncu_summary.py gpurun_out/prof_lift_fwd_cols.ncu-rep > profiles/r01_lift_forward_cols_kernel.txt
 """
 import collections
 import csv
