@@ -172,7 +172,7 @@ static int make_params(const fiery_lift_desc_t* d, const float* calib_a, const f
     P.head_channels = d->channels + (P.use_depth ? d->depth_bins : 0);
     P.calib_mode = d->calib_mode;
     P.calib_a = calib_a; P.calib_b = calib_b; P.fu = fu; P.fv = fv; P.fd = fd;
-    P.accum = nullptr; P.touched = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr;
+    P.accum = nullptr; P.touched = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr; P.head_f16 = nullptr;
     P.bev_layout = d->bev_layout;
     P.pillars = static_cast<long long>(d->bev_x) * d->bev_y;
     P.grid = make_grid_params(*d);
@@ -198,7 +198,7 @@ FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
 
 FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* d) {
     if (!d || d->n_frames <= 0 || d->n_cameras < 1 || d->feat_w < 1) return 0;
-    LiftParams P;
+    LiftParams P = {};
     P.n_frames = d->n_frames; P.n_cameras = d->n_cameras; P.C = d->channels;
     P.n_wtiles = (d->feat_w + WT - 1) / WT;
     P.bev_layout = d->bev_layout;

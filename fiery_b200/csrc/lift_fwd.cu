@@ -248,12 +248,13 @@ int lift_forward_launches(const LiftParams& P) {
 
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch,
                         cudaStream_t stream) {
-    FIERY_REQUIRE(head_dtype == FIERY_DTYPE_F32, "head dtype %d not supported by this build (fp32 only)", head_dtype);
+    FIERY_REQUIRE(head_dtype == FIERY_DTYPE_F32 || head_dtype == FIERY_DTYPE_F16, "head dtype %d not supported (fp32 / fp16)", head_dtype);
     FIERY_REQUIRE(P.C == 64, "channels=%d not supported by this build (C must be 64)", P.C);
     FIERY_REQUIRE(P.D >= 1 && P.D <= 48, "depth_bins=%d not supported by this build (1..48)", P.D);
     FIERY_REQUIRE(P.ww % 4 == 0, "feat_w=%d must be a multiple of 4 (TMA row pitch must be 16-byte aligned)", P.ww);
     int rc = FIERY_OK;
     LiftParams Q = P;
+    Q.head_f16 = head_dtype == FIERY_DTYPE_F16 ? head : nullptr;
     if (P.bev_layout == FIERY_BEV_NHWC) {          // the caller's zero-filled channel-last tensor is the accumulator
         Q.accum = bev_out;
         Q.touched = nullptr;

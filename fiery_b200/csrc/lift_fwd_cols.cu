@@ -22,6 +22,8 @@
 //   * the geometry (pillar of every point, reduced on the fly to run-end events) is evaluated while the TMA is in flight;
 //   * the softmax runs in place on prob (lane = (depth mod 8, column): conflict free, reductions by shuffle);
 //   * run ends are detected warp-uniformly (one 32-bit load + one warp reduction per row, fetched a row ahead).
+#include <string.h>
+
 #include "lift_tile.cuh"
 
 namespace fiery {
@@ -65,6 +67,11 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(smem_addr(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
+}
+
+// 8-byte asynchronous copy global -> shared (SASS LDGSTS.64): one (channel, row) piece = 4 half-precision columns
+__device__ __forceinline__ void cp_async_8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
 
 // packed fp32x2 FMA (SASS FFMA2) on two adjacent columns: acc.lo += a.lo * b.lo, acc.hi += a.hi * b.hi
@@ -159,6 +166,75 @@ __device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const C
     }
 }
 
+// ---- half-precision head tensors (AMP: Encoder.depth_layer emits fp16, encoder.py:96 under PRECISION 16) ------------------------
+// The row pitch of an fp16 plane (w * 2 bytes) is not a multiple of 16 for the reference's w = 60, so the tensor maps cannot
+// describe it; a (channel, row) piece of the tile -- 4 columns = 8 bytes, 8-byte aligned because w and the tile edge are
+// multiples of 4 -- is fetched with one cp.async into the UPPER HALF of the region the fp32 tile will occupy, in the final
+// piece order.  After the geometry phase the pieces are widened in place: every thread reads its pieces, one barrier, every
+// thread writes them as fp32 (exact: fp16 -> fp32 conversion, then the same fp32 arithmetic as for an fp32 head, which is what
+// autocast does to the reference's softmax and outer product, encoder.py:99-100).
+template <int CPL, int NT>
+__device__ __forceinline__ void issue_half_tile(const LiftParams& P, const ColsLayout& L, unsigned char* smem, int img, int w0) {
+    constexpr int LPU = 64 / CPL;
+    const int hh = L.hh;
+    const int n_pp = P.use_depth ? hh * COLS_DPAD : 0;
+    const int n_cp = hh * 64;
+    unsigned char* prob_stage = smem + L.off_prob + hh * COLS_DPAD * WT * 2;     // upper half of prob[row][depth][col4]
+    unsigned char* ctx_stage = smem + L.off_ctx + hh * 64 * WT * 2;              // upper half of ctx[row][k][cl][col4]
+    const __half* head = static_cast<const __half*>(P.head_f16);
+    const size_t plane = static_cast<size_t>(hh) * P.ww;
+    const __half* img_base = head + static_cast<size_t>(img) * P.head_channels * plane + w0;
+    const int ctx_ch0 = P.use_depth ? P.D : 0;
+    for (int p = threadIdx.x; p < n_pp + n_cp; p += NT) {
+        if (p < n_pp) {
+            const int row = p / COLS_DPAD, d = p - row * COLS_DPAD;
+            if (d < P.D) cp_async_8(prob_stage + p * 8, img_base + d * plane + static_cast<size_t>(row) * P.ww);
+        } else {
+            const int q = p - n_pp;
+            const int row = q >> 6, r = q & 63;
+            const int ch = ctx_ch0 + CPL * (r % LPU) + r / LPU;                     // piece order [k][cl], channel = CPL*cl + k
+            cp_async_8(ctx_stage + q * 8, img_base + ch * plane + static_cast<size_t>(row) * P.ww);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int NT>
+__device__ __forceinline__ void widen_half_tile(const LiftParams& P, const ColsLayout& L, unsigned char* smem) {
+    constexpr int MAXP = (32 * (COLS_DPAD + 64) + NT - 1) / NT;                  // pieces per thread at h = 32
+    const int hh = L.hh;
+    const int n_pp = P.use_depth ? hh * COLS_DPAD : 0;
+    const int total = n_pp + hh * 64;
+    unsigned char* prob_base = smem + L.off_prob;
+    unsigned char* ctx_base = smem + L.off_ctx;
+    const int prob_half = hh * COLS_DPAD * WT * 2, ctx_half = hh * 64 * WT * 2;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                  // every thread's pieces have landed
+    uint2 v[MAXP];
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        const int p = threadIdx.x + i * NT;
+        v[i] = make_uint2(0u, 0u);                     // depth slots >= D stay zero (the tensor maps zero-fill them too)
+        if (p < n_pp) {
+            if (p % COLS_DPAD < P.D) v[i] = *reinterpret_cast<const uint2*>(prob_base + prob_half + p * 8);
+        } else if (p < total) {
+            v[i] = *reinterpret_cast<const uint2*>(ctx_base + ctx_half + (p - n_pp) * 8);
+        }
+    }
+    __syncthreads();                                  // all pieces are in registers: the fp32 tile may overwrite them
+#pragma unroll
+    for (int i = 0; i < MAXP; ++i) {
+        const int p = threadIdx.x + i * NT;
+        if (p < total) {
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v[i].x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&v[i].y));
+            float4* dst = reinterpret_cast<float4*>(p < n_pp ? prob_base + p * 16 : ctx_base + (p - n_pp) * 16);
+            *dst = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+    }
+    __syncthreads();                                  // the fp32 tile is complete
+}
+
 // softmax over depth (encoder.py:99) in place on prob[row][d][col]; lane = (d mod 8, col)
 template <int NT>
 __device__ __forceinline__ void softmax_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem) {
@@ -242,7 +318,7 @@ __device__ __forceinline__ void flush_depth(unsigned long long (&acc)[CPL][DD][2
 
 // CPL channels per lane, DD depths per unit: a unit is 64 / CPL lanes, a tile 48 / DD units.
 //   CPL 2, DD 2: 768 threads (a unit is a warp)      CPL 2, DD 4: 384 threads      CPL 4, DD 4: 192 threads (a unit is a half-warp)
-template <int CPL, int DD, int MINB, int UNR = 2>
+template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false>
 __global__ void __launch_bounds__((COLS_DPAD / DD) * (64 / CPL), MINB)
 lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const LiftParams P) {
     constexpr int LPU = 64 / CPL;                     // lanes per unit
@@ -261,7 +337,9 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
     const int hh = L.hh;
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    if (tid == 0) {
+    if (HALF) {
+        issue_half_tile<CPL, NT>(P, L, smem, img, w0);
+    } else if (tid == 0) {
         tma_prefetch_desc(&head_maps.depth);
         tma_prefetch_desc(&head_maps.ctx);
         mbar_init(bar, 1);
@@ -297,7 +375,8 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
         if (P.grid.pow2[0] && P.grid.pow2[1]) stage_geometry_cols<true, NT, DD>(P, L, smem, w0, touched);
         else stage_geometry_cols<false, NT, DD>(P, L, smem, w0, touched);
     }
-    mbar_wait(bar, 0);                                // head tile has landed
+    if (HALF) widen_half_tile<NT>(P, L, smem);         // fp16 pieces -> the fp32 tile, in place
+    else mbar_wait(bar, 0);                           // head tile has landed
     softmax_cols<NT>(P, L, smem);
     __syncthreads();
 
@@ -358,7 +437,7 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
 
 int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams& P, int channels_per_lane);
 
-template <int CPL, int DD, int MINB, int UNR = 2>
+template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false>
 static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStream_t stream) {
     constexpr int NU = COLS_DPAD / DD, NT = NU * (64 / CPL);
     const ColsLayout L(P.hh, P.C, NU);
@@ -367,18 +446,24 @@ static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStre
     FIERY_CUDA_CHECK(cudaGetDevice(&dev_id));
     bool& configured = configured_on[dev_id & 63];
     if (!configured) {
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // ask for the full shared-memory carve-out (3 x 74 KB per SM for the reference shape)
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     FIERY_REQUIRE(L.total <= 227 * 1024, "tile needs %d bytes of shared memory", L.total);
     HeadMapsCols maps;
-    const int rc = encode_head_maps_cols(&maps, head, P, CPL);
-    if (rc != FIERY_OK) return rc;
+    if (HALF) {
+        memset(&maps, 0, sizeof(maps));              // unused: half-precision tiles are fetched with cp.async
+        FIERY_REQUIRE(P.head_f16 != nullptr && (reinterpret_cast<uintptr_t>(P.head_f16) & 7) == 0,
+                      "half-precision head tensor must be 8-byte aligned");
+    } else {
+        const int rc = encode_head_maps_cols(&maps, head, P, CPL);
+        if (rc != FIERY_OK) return rc;
+    }
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
-    lift_forward_cols_kernel<CPL, DD, MINB, UNR><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
+    lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }
@@ -412,6 +497,10 @@ int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stre
         default: break;
     }
 #endif
+    if (P.head_f16) {
+        if (variant == 2) return launch_forward_cols_t<2, 3, 2, 2, true>(P, head, stream);
+        return launch_forward_cols_t<2, 2, 2, 1, true>(P, head, stream);
+    }
     if (variant == 2) return launch_forward_cols_t<2, 3, 2>(P, head, stream);
     return launch_forward_cols_t<2, 2, 2, 1>(P, head, stream);
 }

@@ -31,6 +31,7 @@ struct LiftParams {
     const float* fu;         // (w) frustum pixel column coordinate   fiery.py:120
     const float* fv;         // (h) frustum pixel row coordinate      fiery.py:122
     const float* fd;         // (D) frustum depth                     fiery.py:115
+    const void* head_f16;    // forward, half-precision head tensor (fetched with cp.async; fp32 heads come through the tensor maps)
     float* accum;            // forward: (B', X*Y, C) channel-last accumulation target
     unsigned char* touched;  // forward, NCHW output: (B', X*Y) byte map of pillars that received a point
     const float* grad_bev;   // backward: (B', X*Y, C) or (B', C, X*Y)

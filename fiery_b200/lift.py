@@ -12,6 +12,7 @@ grid tensors, under the same names, so a reference ``state_dict`` loads into it 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -23,6 +24,11 @@ from .geometry import (_require_cuda, _stream_ptr, bev_offset_fp32, calculate_bi
                        split_frustum, z_valid_interval)
 
 _TORCH_TO_DTYPE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
+
+# Half-precision head tensors (AMP, baseline.yml PRECISION 16): True = the forward tile kernel reads the fp16 tensor itself
+# (cp.async pieces widened in shared memory); False = the tensor is widened to fp32 on the device first.  Both compute the
+# same fp32 arithmetic on exactly converted values.  Overridable with FIERY_B200_NATIVE_FP16=0/1.
+NATIVE_FP16_FORWARD = os.environ.get("FIERY_B200_NATIVE_FP16", "0") == "1"
 
 
 def pack_sequence_dim(x: torch.Tensor) -> torch.Tensor:
@@ -359,18 +365,22 @@ class _LiftSplatFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, head, intrinsics, extrinsics, module: LiftSplat):
         # Under AMP (baseline.yml PRECISION 16) depth_layer emits fp16; the reference's softmax autocasts to fp32 and the
-        # fp32 x fp16 outer product promotes to fp32 (encoder.py:99-100), so the lift itself is fp32 there too.  This build's
-        # kernels read an fp32 head tensor: half-precision logits are widened on the device first.
+        # fp32 x fp16 outer product promotes to fp32 (encoder.py:99-100), so the lift itself is fp32 there too.  The forward
+        # tile kernel can read the fp16 tensor itself (NATIVE_FP16_FORWARD); otherwise, and for bf16, the logits are widened
+        # on the device first.  The backward kernel always reads fp32.
         ctx.head_dtype = head.dtype
-        head32 = head if head.dtype == torch.float32 else head.float()
-        out = module._launch_forward(head32, intrinsics, extrinsics)
+        native = head.dtype == torch.float32 or (head.dtype == torch.float16 and NATIVE_FP16_FORWARD)
+        head_in = head if native else head.float()
+        out = module._launch_forward(head_in, intrinsics, extrinsics)
         ctx.module = module
-        ctx.save_for_backward(head32, intrinsics, extrinsics)
+        ctx.save_for_backward(head_in, intrinsics, extrinsics)
         return out
 
     @staticmethod
     def backward(ctx, grad_bev):
         head, intrinsics, extrinsics = ctx.saved_tensors
+        if head.dtype != torch.float32:
+            head = head.float()                      # the backward kernel reads an fp32 head tensor
         grad_head = ctx.module._launch_backward(head, intrinsics, extrinsics, grad_bev)
         return grad_head.to(ctx.head_dtype), None, None, None     # calibration is data: no gradient (geometry.py:300)
 

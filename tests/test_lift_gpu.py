@@ -4,6 +4,8 @@ Bar (BASELINE.json north_star): bit-exact integer rank/geometry indices; BEV fea
 The reference's own cumsum path is noisier than 1e-4 element-wise (hard part 1), so values are
 compared normwise / max-abs-scaled against the oracle AND against the fp64 exact pooling.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -334,6 +336,43 @@ def test_reference_call_site_signature_and_amp_head():
     assert O.normwise_error(bev16.detach().cpu(), exact16) < TOL
     bev16.sum().backward()
     assert h16.grad.dtype == torch.float16
+
+
+@pytest.mark.parametrize("name,frames,use_depth", [("cfg1_tiny", 2, True), ("cfg1_tiny", 1, False), ("cfg2_static_lss", 1, True),
+                                                    ("cfg3_baseline", 9, True)])
+@pytest.mark.skipif(os.environ.get("FIERY_B200_TEST_FP16", "0") != "1", reason="native fp16 head path: opt-in until validated on a B200")
+def test_half_precision_head_read_by_the_tile_kernel(name, frames, use_depth):
+    """fp16 head tensor (AMP, baseline.yml PRECISION 16) through fiery_lift_forward with FIERY_DTYPE_F16: the tile kernel fetches
+    the fp16 pieces itself and widens them in shared memory.  Must equal the lift of the exactly widened fp32 tensor (same
+    arithmetic; only the accumulation order differs) and match the exact pooling of those values."""
+    from fiery_b200 import lift as lift_mod
+    cfg = LiftConfig(**{**CONFIGS[name].__dict__, "frames": frames, "use_depth_distribution": use_depth})
+    dev = _dev()
+    K, E = make_calibration(cfg, seed=41)
+    Kd, Ed = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
+    h16 = torch.from_numpy(make_head(cfg, seed=41)).to(dev).half()
+    lift = LiftSplat.from_config(cfg).to(dev)
+    with torch.no_grad():
+        widened = lift(h16.float(), Kd, Ed)
+        native = lift._launch_forward(h16, Kd, Ed)               # DTYPE_F16 through the C ABI
+    assert native.dtype == torch.float32
+    assert O.normwise_error(native.cpu(), widened.cpu()) < 1e-6
+    if frames <= 2:
+        exact = O.LiftOracle.from_config(cfg).lift_exact(h16.float().cpu(), torch.from_numpy(K), torch.from_numpy(E))
+        assert O.normwise_error(native.cpu(), exact) < TOL
+    # the autograd path with the switch on: fp16 in, fp32 BEV, fp16 gradient, same values as the widened path
+    old = lift_mod.NATIVE_FP16_FORWARD
+    lift_mod.NATIVE_FP16_FORWARD = True
+    try:
+        a = h16.clone().requires_grad_(True)
+        out = lift(a, Kd, Ed)
+        out.sum().backward()
+    finally:
+        lift_mod.NATIVE_FP16_FORWARD = old
+    b = h16.clone().requires_grad_(True)
+    lift(b, Kd, Ed).sum().backward()
+    assert a.grad.dtype == torch.float16 and torch.equal(a.grad, b.grad)
+    assert O.normwise_error(out.detach().cpu(), widened.cpu()) < 1e-6
 
 
 def test_all_points_masked_and_degenerate_calibration():
