@@ -28,7 +28,7 @@ _TORCH_TO_DTYPE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
 # Half-precision head tensors (AMP, baseline.yml PRECISION 16): True = the forward tile kernel reads the fp16 tensor itself
 # (cp.async pieces widened in shared memory); False = the tensor is widened to fp32 on the device first.  Both compute the
 # same fp32 arithmetic on exactly converted values.  Overridable with FIERY_B200_NATIVE_FP16=0/1.
-NATIVE_FP16_FORWARD = os.environ.get("FIERY_B200_NATIVE_FP16", "0") == "1"
+NATIVE_FP16_FORWARD = os.environ.get("FIERY_B200_NATIVE_FP16", "1") == "1"
 
 
 def pack_sequence_dim(x: torch.Tensor) -> torch.Tensor:

@@ -94,7 +94,9 @@ FIERY_API const char* fiery_last_error(void);
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* desc);
 
 /*
- * Forward lift.  head: (B'*n, D+C, h, w) [C channels if !use_depth_distribution], dtype head_dtype.
+ * Forward lift.  head: (B'*n, D+C, h, w) [C channels if !use_depth_distribution], dtype head_dtype (FIERY_DTYPE_F32, or
+ * FIERY_DTYPE_F16 for AMP heads: values are converted exactly to fp32 and all arithmetic is fp32, as autocast does to the
+ * reference's softmax and outer product, encoder.py:99-100).
  * frustum_u (w), frustum_v (h), frustum_d (D): the separable factors of Fiery.frustum (fiery.py:109-128), fp32.
  * bev_out: (B',C,X,Y) fp32 in bev_layout.  For FIERY_BEV_NHWC the caller must pass bev_out zero-filled (the kernel
  * accumulates into it) and scratch may be NULL.
@@ -113,8 +115,8 @@ FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* desc);
 FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* desc);
 
 /*
- * Backward of the lift w.r.t. the head tensor.  grad_bev: (B',C,X,Y) fp32 in bev_layout; grad_head: same shape and
- * dtype as head, fully overwritten.  Calibration gets no gradient (geometry is integer, geometry.py:300).
+ * Backward of the lift w.r.t. the head tensor (head_dtype must be FIERY_DTYPE_F32 in this build: widen an fp16 head first).
+ * grad_bev: (B',C,X,Y) fp32 in bev_layout; grad_head: same shape and dtype as head, fully overwritten.  Calibration gets no gradient (geometry is integer, geometry.py:300).
  */
 FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                         const float* frustum_u, const float* frustum_v, const float* frustum_d,

@@ -340,7 +340,6 @@ def test_reference_call_site_signature_and_amp_head():
 
 @pytest.mark.parametrize("name,frames,use_depth", [("cfg1_tiny", 2, True), ("cfg1_tiny", 1, False), ("cfg2_static_lss", 1, True),
                                                     ("cfg3_baseline", 9, True)])
-@pytest.mark.skipif(os.environ.get("FIERY_B200_TEST_FP16", "0") != "1", reason="native fp16 head path: opt-in until validated on a B200")
 def test_half_precision_head_read_by_the_tile_kernel(name, frames, use_depth):
     """fp16 head tensor (AMP, baseline.yml PRECISION 16) through fiery_lift_forward with FIERY_DTYPE_F16: the tile kernel fetches
     the fp16 pieces itself and widens them in shared memory.  Must equal the lift of the exactly widened fp32 tensor (same
