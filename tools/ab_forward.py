@@ -71,12 +71,11 @@ best = min((v for v in res["tile"] if "us_mean" in res["tile"][v] and res["tile"
 res["best_tile"] = best
 out_nchw = torch.empty((F, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
 ref_nchw = ref.permute(0, 3, 1, 2)
-combos = os.environ.get("AB_COMBOS", "4:148:0 4:148:1 4:148:0 4:148:1 4:90:1").split()
+combos = os.environ.get("AB_COMBOS", "1:148 2:148 4:148").split()
 from fiery_b200.synthetic import make_grad_bev
 gout = torch.from_numpy(make_grad_bev(cfg, seed=100)).to(dev)
 for combo in combos:
-    chains, min_tiles, tail = (int(x) for x in combo.split(":"))
-    os.environ["FIERY_CHAIN_TAIL"] = str(tail)
+    chains, min_tiles = (int(x) for x in combo.split(":"))
     os.environ["FIERY_COLS_VARIANT"] = "-1"
     os.environ["FIERY_CHAINS"] = str(chains)
     os.environ["FIERY_CHAIN_MIN_TILES"] = str(min_tiles)
@@ -118,7 +117,7 @@ for combo in combos:
     res["layout_pass"][combo] = {"us_mean": mean, "graph_us_mean": gmean, "graph_us_min": gmn, "rel_err": max(err, err2),
                                  "scratch_clean": clean and clean2, "launches": int(lib.fiery_lift_forward_launches(desc)),
                                  "bwd_us_mean": bmean, "bwd_rel_err_vs_first": berr}
-    print("chains:min_tiles:short_tail", combo, res["layout_pass"][combo], flush=True)
+    print("chains:min_tiles", combo, res["layout_pass"][combo], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", f"ab_{wl}.json"), "w") as fh:
     json.dump(res, fh, indent=1)

@@ -7,7 +7,7 @@ for w in cfg2_static_lss_b8 cfg3_baseline cfg4_pon; do
   echo "== $w"; timeout 600 python tools/ab_forward.py $w 2>&1 | grep -E "^tile|^chains|Error|error" | cut -c1-330
 done
 for combo in $AB_TEST; do
-  IFS=: read ch mt vec <<< "$combo"
+  IFS=: read ch mt <<< "$combo"
   echo "== parity tests with $ch chains, >= $mt tiles per group"
-  FIERY_CHAINS=$ch FIERY_CHAIN_MIN_TILES=$mt FIERY_CHAIN_TAIL=$vec timeout 600 python -m pytest tests/test_lift_gpu.py -m gpu -q --no-header -x 2>&1 | tail -3
+  FIERY_CHAINS=$ch FIERY_CHAIN_MIN_TILES=$mt timeout 600 python -m pytest tests/test_lift_gpu.py -m gpu -q --no-header -x 2>&1 | tail -3
 done
