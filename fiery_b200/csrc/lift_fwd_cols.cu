@@ -90,6 +90,62 @@ __device__ __forceinline__ void clear_half(unsigned long long& v, unsigned keep)
     v &= HALF ? ((static_cast<unsigned long long>(keep) << 32) | 0xffffffffull) : (0xffffffff00000000ull | keep);
 }
 
+// ---- packed fp32x2 arithmetic for the geometry of TWO rows at a time (experiment builds, FIERY_COLS_AB) ------------------------
+// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (and even fma(p, 1, c)), which would break the reference's separate
+// roundings; a chain of scalar FMUL feeding packed FADD2 survives (checked in SASS): products are formed per row with
+// __fmul_rn, everything additive runs packed.  add.rn.f32x2 / mul.rn.f32x2 round each half like the scalar instruction.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
+// pillars (rank or -1) of rows (v0, v1) of one (column, depth) pair: the arithmetic of ego_point / select_pillar, two at a time
+template <bool POW2>
+__device__ __forceinline__ void pillars_of_two_rows(const CameraTransform& T, const ColumnTerms& ct, float v0, float v1, float depth,
+                                                    float offx, float offy, float offz, float kx, float ky, float Xf, float Yf,
+                                                    float z_lo, float z_hi, int Y, int& cur0, int& cur1) {
+    const unsigned long long vd = f2_mul(f2_pack(v0, v1), f2_pack(depth, depth));           // v*d, fiery.py:202
+    float vd0, vd1;
+    f2_unpack(vd, vd0, vd1);
+    unsigned long long p[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const unsigned long long prod = f2_pack(__fmul_rn(T.m[r * 3 + 1], vd0), __fmul_rn(T.m[r * 3 + 1], vd1));
+        unsigned long long acc = f2_add(f2_pack(ct.a[r], ct.a[r]), prod);                    // (M[r][0]*(u*d) + M[r][1]*(v*d))
+        acc = f2_add(acc, f2_pack(ct.c[r], ct.c[r]));                                        //  + M[r][2]*d
+        p[r] = f2_add(acc, f2_pack(T.t[r], T.t[r]));                                         //  + t_r          fiery.py:204-205
+    }
+    // p - off == p + (-off) exactly
+    const unsigned long long ax = f2_add(p[0], f2_pack(-offx, -offx)), ay = f2_add(p[1], f2_pack(-offy, -offy));
+    const unsigned long long az = f2_add(p[2], f2_pack(-offz, -offz));
+    float sx0, sx1, sy0, sy1, az0, az1;
+    if (POW2) {
+        f2_unpack(f2_mul(ax, f2_pack(kx, kx)), sx0, sx1);                                    // exact scale, fiery.py:236
+        f2_unpack(f2_mul(ay, f2_pack(ky, ky)), sy0, sy1);
+    } else {
+        float a0, a1;
+        f2_unpack(ax, a0, a1); sx0 = __fdiv_rn(a0, kx); sx1 = __fdiv_rn(a1, kx);
+        f2_unpack(ay, a0, a1); sy0 = __fdiv_rn(a0, ky); sy1 = __fdiv_rn(a1, ky);
+    }
+    f2_unpack(az, az0, az1);
+    cur0 = select_pillar(sx0, sy0, az0, Xf, Yf, z_lo, z_hi, static_cast<int>(sx0) * Y + static_cast<int>(sy0));
+    cur1 = select_pillar(sx1, sy1, az1, Xf, Yf, z_lo, z_hi, static_cast<int>(sx1) * Y + static_cast<int>(sy1));
+}
+
 // Geometry of the tile: the pillar (rank, fiery.py:236-256; -1 = masked) of every point, evaluated with the reference
 // arithmetic, reduced on the fly to what the pooling loop consumes:
 //   ev[unit][row]      bit j (slot j = dd*4 + col: depth DD*unit + dd, column col) set <=> pair j changes pillar between
@@ -98,7 +154,7 @@ __device__ __forceinline__ void clear_half(unsigned long long& v, unsigned keep)
 //   pillar[row][pair]  written only where it is read: the last row of every run
 //   touched[pillar]    the layout pass's map of pillars that receive something, marked at every run start
 // thread = (pair, row range); the NRS ranges of a pair sit in adjacent lanes and hand their last pillar to the next range.
-template <bool POW2, int NT, int DD>
+template <bool POW2, int NT, int DD, bool PACKED = false>
 __device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem, int w0,
                                                     unsigned char* touched) {
     constexpr int NRS = NT / COLS_NPAIR >= 4 ? 4 : (NT / COLS_NPAIR >= 2 ? 2 : 1);
@@ -141,8 +197,19 @@ __device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const C
     if (!dead && h_lo < h_hi) {
         const float depth = s_d[d];
         const ColumnTerms ct = column_terms(T, s_u[col], depth);
+        int h = h_lo;
+        if (PACKED) {                                                         // two rows per trip, packed adds
+            for (; h + 1 < h_hi; h += 2) {
+                int cur0, cur1;
+                pillars_of_two_rows<POW2>(T, ct, s_v[h], s_v[h + 1], depth, offx, offy, offz, kx, ky, Xf, Yf, z_lo, z_hi, Y, cur0, cur1);
+                if (h == h_lo) first = cur0;
+                else if (cur0 != prev) run_ends(h, prev, cur0);
+                if (cur1 != cur0) run_ends(h + 1, cur0, cur1);
+                prev = cur1;
+            }
+        }
 #pragma unroll 2
-        for (int h = h_lo; h < h_hi; ++h) {
+        for (; h < h_hi; ++h) {
             float p[3];
             ego_point(T, ct, s_v[h], depth, p);                               // fiery.py:199-205
             const float ax = __fsub_rn(p[0], offx), ay = __fsub_rn(p[1], offy), az = __fsub_rn(p[2], offz);
@@ -318,7 +385,7 @@ __device__ __forceinline__ void flush_depth(unsigned long long (&acc)[CPL][DD][2
 
 // CPL channels per lane, DD depths per unit: a unit is 64 / CPL lanes, a tile 48 / DD units.
 //   CPL 2, DD 2: 768 threads (a unit is a warp)      CPL 2, DD 4: 384 threads      CPL 4, DD 4: 192 threads (a unit is a half-warp)
-template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false>
+template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false, bool PACKED = false>
 __global__ void __launch_bounds__((COLS_DPAD / DD) * (64 / CPL), MINB)
 lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const LiftParams P) {
     constexpr int LPU = 64 / CPL;                     // lanes per unit
@@ -372,8 +439,8 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
     __syncthreads();                                  // constants, camera and the mbarrier are set up
     {
         unsigned char* touched = P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
-        if (P.grid.pow2[0] && P.grid.pow2[1]) stage_geometry_cols<true, NT, DD>(P, L, smem, w0, touched);
-        else stage_geometry_cols<false, NT, DD>(P, L, smem, w0, touched);
+        if (P.grid.pow2[0] && P.grid.pow2[1]) stage_geometry_cols<true, NT, DD, PACKED>(P, L, smem, w0, touched);
+        else stage_geometry_cols<false, NT, DD, PACKED>(P, L, smem, w0, touched);
     }
     if (HALF) widen_half_tile<NT>(P, L, smem);         // fp16 pieces -> the fp32 tile, in place
     else mbar_wait(bar, 0);                           // head tile has landed
@@ -437,7 +504,7 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
 
 int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams& P, int channels_per_lane);
 
-template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false>
+template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false, bool PACKED = false>
 static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStream_t stream) {
     constexpr int NU = COLS_DPAD / DD, NT = NU * (64 / CPL);
     const ColsLayout L(P.hh, P.C, NU);
@@ -446,9 +513,9 @@ static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStre
     FIERY_CUDA_CHECK(cudaGetDevice(&dev_id));
     bool& configured = configured_on[dev_id & 63];
     if (!configured) {
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // ask for the full shared-memory carve-out (3 x 74 KB per SM for the reference shape)
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
@@ -463,7 +530,7 @@ static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStre
         if (rc != FIERY_OK) return rc;
     }
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
-    lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
+    lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PACKED><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }
@@ -494,6 +561,8 @@ int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stre
         case 6: return launch_forward_cols_t<4, 3, 3>(P, head, stream);
         case 7: return launch_forward_cols_t<2, 4, 3>(P, head, stream);
         case 8: return launch_forward_cols_t<2, 2, 2, 2>(P, head, stream);
+        case 12: return launch_forward_cols_t<2, 2, 2, 1, false, true>(P, head, stream);     // packed geometry
+        case 13: return launch_forward_cols_t<2, 3, 2, 2, false, true>(P, head, stream);
         default: break;
     }
 #endif
