@@ -177,6 +177,9 @@ def main():
     # (single_timeframe.yml:8), the configuration the metric is quoted on; cfg3_baseline (9 frames) etc. via --workload
     ap.add_argument("--workload", default="cfg2_static_lss_b8", choices=sorted(CONFIGS))
     ap.add_argument("--layout", default="contiguous", choices=["contiguous", "channels_last"])
+    ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"],
+                    help="dtype of the head tensor: f32 (the metric's definition) or f16 (AMP heads, baseline.yml PRECISION 16: the "
+                         "forward tile kernel reads the half-precision tensor itself; all arithmetic stays fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per upload/lift/download pipeline stage in the e2e run")
     ap.add_argument("--cpu-frames", type=int, default=3)
@@ -212,6 +215,9 @@ def main():
     lift = LiftSplat.from_config(cfg, output_layout=args.layout).to(dev)
     K_d, E_d = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
     head_d = torch.from_numpy(head_np).to(dev)
+    head_dtype = torch.float16 if args.head_dtype == "f16" else torch.float32
+    if head_dtype != torch.float32:
+        head_d = head_d.to(head_dtype)
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     W, S = max(args.warmup, 3), max(args.steps, 1)
 
@@ -272,7 +278,7 @@ def main():
     barrier()
 
     # ---- e2e: pinned host inputs, host copy of the result, all inside the timed region ---------------------------------
-    head_h = torch.from_numpy(head_np).pin_memory()
+    head_h = torch.from_numpy(head_np).to(head_dtype).pin_memory()
     K_h, E_h = torch.from_numpy(K).pin_memory(), torch.from_numpy(E).pin_memory()
     X, Y = cfg.bev_hw
     out_h = torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32).pin_memory()
@@ -294,7 +300,7 @@ def main():
     stream = _stream_ptr(dev)
 
     def make_kernel_only(layout_code, out_tensor):
-        desc = lift._desc(c, frames, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, layout_code)
+        desc = lift._desc(c, frames, cfg.n_cameras, head_dtype, _lib.CALIB_RAW, layout_code)
         scratch = torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
 
         def run():
@@ -304,7 +310,7 @@ def main():
         return run, scratch
 
     launches_per_step = int(lib.fiery_lift_forward_launches(
-        lift._desc(c, frames, cfg.n_cameras, torch.float32, _lib.CALIB_RAW,
+        lift._desc(c, frames, cfg.n_cameras, head_dtype, _lib.CALIB_RAW,
                    _lib.BEV_NHWC if args.layout == "channels_last" else _lib.BEV_NCHW)))
     out_nchw = torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
     acc_nhwc = torch.zeros((frames, X, Y, cfg.out_channels), dtype=torch.float32, device=dev)
@@ -399,7 +405,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        alg_bytes = cfg.fwd_bytes_per_frame() * frames
+        alg_bytes = cfg.fwd_bytes_per_frame(head_itemsize=head_d.element_size()) * frames
         achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": S,
@@ -411,18 +417,19 @@ def main():
             "config": {"workload": cfg.name, "frames_per_step_per_gpu": frames, "n_cameras": cfg.n_cameras,
                        "final_dim": list(cfg.final_dim), "feat_hw": list(cfg.feat_hw), "depth_bins": cfg.depth_bins,
                        "channels": cfg.out_channels, "bev": [X, Y], "direction": "forward", "output_layout": args.layout,
+                       "head_dtype": args.head_dtype,
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                        "l2": "flushed before every timed step (256 MiB write); step time = CUDA events around the step",
                        "api": "value: LiftSplat.capture() CUDA-graph replay; value_eager: LiftSplat.forward; "
                               "e2e: LiftSplat.lift_from_host (pinned host in/out, 3-stream chunk pipeline)",
                        "timing": "mean over steps, max over ranks"},
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
-                    "h2d_bytes_per_step": int(head_h.numel() * 4 + K_h.numel() * 4 + E_h.numel() * 4),
+                    "h2d_bytes_per_step": int(head_h.numel() * head_h.element_size() + K_h.numel() * 4 + E_h.numel() * 4),
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},
             # kernels of the timed `value` region: per step, one tile kernel (+ one layout pass) per frame group
             "gpu_launches": launches_per_step * S,
             "roofline": {"bound": "hbm", "kernel": "lift_forward_cols_kernel", "achieved": achieved, "peak": peak,
-                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(cfg.name),
+                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(cfg.name) if args.head_dtype == "f32" else None,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "lift_plus_finalize_ms": ms_both,
                          "step_frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / peak},
             "clocks": clocks,
@@ -438,10 +445,11 @@ def main():
             # GPU -- the GPU-vs-GPU comparison SURVEY.md section 8d asks for next to the CPU number; baseline only
             from oracle import lift_oracle as O
             o_gpu = O.LiftOracle.from_config(cfg).to(dev)
+            head_ref = head_d.float()                     # the reference's chain is timed on fp32 values
             with torch.no_grad():
                 for _ in range(2):
-                    o_gpu.lift(head_d, K_d, E_d)
-                t_ref_gpu = timed_steps(lambda: o_gpu.lift(head_d, K_d, E_d), 5)
+                    o_gpu.lift(head_ref, K_d, E_d)
+                t_ref_gpu = timed_steps(lambda: o_gpu.lift(head_ref, K_d, E_d), 5)
             line["reference_ops_on_gpu"] = {"value": frames / (float(np.mean(t_ref_gpu)) * 1e-3), "unit": "frames/s",
                                             "ms_per_step": float(np.mean(t_ref_gpu)),
                                             "what": "oracle/lift_oracle.py (the reference's PyTorch op chain) on CUDA tensors, "
