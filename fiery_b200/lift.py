@@ -284,6 +284,8 @@ class LiftSplat(nn.Module):
         ch = C + (c["D"] if self.use_depth_distribution else 0)
         if tuple(head.shape) != (B * n, ch, c["h"], c["w"]):
             raise ValueError(f"head must be {(B * n, ch, c['h'], c['w'])}, got {tuple(head.shape)}")
+        if head.dtype != torch.float32 and not (head.dtype == torch.float16 and NATIVE_FP16_FORWARD):
+            head = head.float()                      # half-precision heads: widen first (see NATIVE_FP16_FORWARD)
         head = head.contiguous()
         mode, a, b = self._calibration(intrinsics.to(dev), extrinsics.to(dev))
         X, Y, _ = c["dim"]

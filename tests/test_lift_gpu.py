@@ -351,16 +351,22 @@ def test_half_precision_head_read_by_the_tile_kernel(name, frames, use_depth):
     Kd, Ed = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
     h16 = torch.from_numpy(make_head(cfg, seed=41)).to(dev).half()
     lift = LiftSplat.from_config(cfg).to(dev)
+    old = lift_mod.NATIVE_FP16_FORWARD
     with torch.no_grad():
         widened = lift(h16.float(), Kd, Ed)
-        native = lift._launch_forward(h16, Kd, Ed)               # DTYPE_F16 through the C ABI
-    assert native.dtype == torch.float32
+        lift_mod.NATIVE_FP16_FORWARD = True
+        try:
+            native = lift._launch_forward(h16, Kd, Ed)           # DTYPE_F16 through the C ABI
+        finally:
+            lift_mod.NATIVE_FP16_FORWARD = old
+        default = lift._launch_forward(h16, Kd, Ed)              # default: widened on the device first
+    assert native.dtype == torch.float32 and default.dtype == torch.float32
+    assert O.normwise_error(default.cpu(), widened.cpu()) < 1e-6
     assert O.normwise_error(native.cpu(), widened.cpu()) < 1e-6
     if frames <= 2:
         exact = O.LiftOracle.from_config(cfg).lift_exact(h16.float().cpu(), torch.from_numpy(K), torch.from_numpy(E))
         assert O.normwise_error(native.cpu(), exact) < TOL
     # the autograd path with the switch on: fp16 in, fp32 BEV, fp16 gradient, same values as the widened path
-    old = lift_mod.NATIVE_FP16_FORWARD
     lift_mod.NATIVE_FP16_FORWARD = True
     try:
         a = h16.clone().requires_grad_(True)
