@@ -86,6 +86,10 @@ CONFIGS = {
     "cfg3_baseline": LiftConfig("cfg3_baseline", frames=9),
     # literature/pon_setting.yml: 400x200 @ 25 cm, batch 4 x 3
     "cfg4_pon": LiftConfig("cfg4_pon", x_bound=(-50.0, 50.0, 0.25), y_bound=(-25.0, 25.0, 0.25), frames=12),
+    # not a reference YAML: cell sizes that are no powers of two, so s = (p - off) / res takes the true-division path
+    # (fiery.py:236) instead of the exact scale -- a parity case, not a bench workload
+    "cfg6_res_0p4_0p3": LiftConfig("cfg6_res_0p4_0p3", n_cameras=2, final_dim=(64, 160), x_bound=(-50.0, 50.0, 0.4),
+                                   y_bound=(-30.0, 30.0, 0.3), frames=2),
 }
 
 

@@ -140,7 +140,7 @@ def main():
     # ---- a7: BEV parameters ------------------------------------------------------------------------------
     print("BEV parameters")
     params = {}
-    for cname in ("cfg1_tiny", "cfg2_static_lss", "cfg4_pon"):
+    for cname in ("cfg1_tiny", "cfg2_static_lss", "cfg4_pon", "cfg6_res_0p4_0p3"):
         cfg = CONFIGS[cname]
         r, s0, d = bev_params(list(cfg.x_bound), list(cfg.y_bound), list(cfg.z_bound))
         ro, so, do = O.bev_grid(cfg.x_bound, cfg.y_bound, cfg.z_bound)
@@ -150,7 +150,7 @@ def main():
     # ---- full path, per config -----------------------------------------------------------------------------
     lift = dict(params)
     cases = [("cfg1_tiny", 0.02, 1), ("cfg1_tiny", 0.0, 1), ("cfg2_static_lss", 0.02, 1), ("cfg2_static_lss", 0.0, 1),
-             ("cfg4_pon", 0.02, 1), ("cfg3_baseline", 0.02, 2)]
+             ("cfg4_pon", 0.02, 1), ("cfg3_baseline", 0.02, 2), ("cfg6_res_0p4_0p3", 0.02, 2), ("cfg6_res_0p4_0p3", 0.0, 2)]
     for cname, jitter, frames in cases:
         base = CONFIGS[cname]
         cfg = LiftConfig(**{**base.__dict__, "frames": frames})

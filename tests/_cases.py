@@ -8,7 +8,7 @@ from fiery_b200.synthetic import CONFIGS, LiftConfig, make_calibration, make_gra
 
 # (config name, calibration jitter in rad, frames) -- must match oracle/gen_golden.py:main
 GOLDEN_CASES = [("cfg1_tiny", 0.02, 1), ("cfg1_tiny", 0.0, 1), ("cfg2_static_lss", 0.02, 1), ("cfg2_static_lss", 0.0, 1),
-                ("cfg4_pon", 0.02, 1), ("cfg3_baseline", 0.02, 2)]
+                ("cfg4_pon", 0.02, 1), ("cfg3_baseline", 0.02, 2), ("cfg6_res_0p4_0p3", 0.02, 2), ("cfg6_res_0p4_0p3", 0.0, 2)]
 
 
 def case_id(case):
