@@ -197,6 +197,9 @@ __global__ void compose_calibration_kernel(int n, const float* __restrict__ K, c
 int lift_chunk_frames(int n_frames, long long pillars, int channels) {
     const long long per_frame = pillars * channels * 4 + pillars;
     long long c = (1ll << 30) / (per_frame > 0 ? per_frame : 1);
+#ifdef FIERY_COLS_AB
+    if (const char* e = getenv("FIERY_CHUNK_FRAMES")) c = atoi(e);   // experiment builds: force the multi-chunk path on small batches
+#endif
     if (c < 1) c = 1;
     if (c > n_frames) c = n_frames;
     return static_cast<int>(c < 1 ? 1 : c);
