@@ -151,10 +151,14 @@ def main():
     lift = dict(params)
     cases = [("cfg1_tiny", 0.02, 1), ("cfg1_tiny", 0.0, 1), ("cfg2_static_lss", 0.02, 1), ("cfg2_static_lss", 0.0, 1),
              ("cfg4_pon", 0.02, 1), ("cfg3_baseline", 0.02, 2), ("cfg6_res_0p4_0p3", 0.02, 2), ("cfg6_res_0p4_0p3", 0.0, 2)]
-    for cname, jitter, frames in cases:
+    # the configurations bench.py quotes, at their full batch (BASELINE.json configs[1..3]): tag carries the frame count
+    bench_cases = [("cfg2_static_lss_b8", 0.02, 8), ("cfg3_baseline", 0.02, 9), ("cfg4_pon", 0.02, 12)]
+    for cname, jitter, frames in cases + bench_cases:
         base = CONFIGS[cname]
         cfg = LiftConfig(**{**base.__dict__, "frames": frames})
         tag = f"{cname}__j{int(jitter * 1000):03d}"
+        if (cname, jitter, frames) in bench_cases:
+            tag += f"__f{frames}"
         print(f"lift {tag}")
         Knp, Enp = make_calibration(cfg, seed=3, jitter_rad=jitter)
         head_np = make_head(cfg, seed=3)

@@ -11,12 +11,17 @@ GOLDEN_CASES = [("cfg1_tiny", 0.02, 1), ("cfg1_tiny", 0.0, 1), ("cfg2_static_lss
                 ("cfg4_pon", 0.02, 1), ("cfg3_baseline", 0.02, 2), ("cfg6_res_0p4_0p3", 0.02, 2), ("cfg6_res_0p4_0p3", 0.0, 2)]
 
 
+# the configurations bench.py quotes, at their full batch; golden tags carry the frame count
+BENCH_CASES = [("cfg2_static_lss_b8", 0.02, 8), ("cfg3_baseline", 0.02, 9), ("cfg4_pon", 0.02, 12)]
+
+
 def case_id(case):
     return f"{case[0]}-j{int(case[1] * 1000):03d}-f{case[2]}"
 
 
 def golden_tag(case):
-    return f"{case[0]}__j{int(case[1] * 1000):03d}"
+    tag = f"{case[0]}__j{int(case[1] * 1000):03d}"
+    return tag + f"__f{case[2]}" if tuple(case) in BENCH_CASES else tag
 
 
 def build_case(case, seed=3):

@@ -135,3 +135,25 @@ def test_c_restatement_agrees(golden_lift, case):
     bev = c_oracle.pool_exact(prob, head[:, D:].double().numpy(), idx, keep, cfg.n_cameras, X, Y)
     exact = oracle.lift_exact(head, K, E, combined=torch.from_numpy(comb))
     assert O.normwise_error(torch.from_numpy(bev), exact) < 1e-13
+
+
+@pytest.mark.parametrize("case", __import__("tests._cases", fromlist=["BENCH_CASES"]).BENCH_CASES, ids=case_id)
+def test_indices_at_bench_configs_match_reference(golden_lift, case):
+    """The configurations bench.py quotes (8 / 9 / 12 frames): the oracle's voxel indices of every frame -- torch ops and the C
+    restatement -- hash to what the reference recorded (fiery.py:236-256)."""
+    from oracle import c_oracle
+    cfg, K, E, _, _ = build_case(case)
+    tag = golden_tag(case)
+    oracle = O.LiftOracle.from_config(cfg)
+    comb, trans = golden_lift[f"{tag}__combined"], golden_lift[f"{tag}__translation"]
+    ce, te = O.compose_calibration_explicit(K.numpy(), E.numpy())
+    assert np.array_equal(ce, comb) and np.array_equal(te, trans)
+    idx, keep = oracle.point_indices(K, E, combined=torch.from_numpy(comb))
+    assert sha(idx.numpy()) == golden_str(golden_lift[f"{tag}__idx_sha256"])
+    assert sha(keep.numpy()) == golden_str(golden_lift[f"{tag}__keep_sha256"])
+    fr = oracle.frustum
+    off = (oracle.start - oracle.resolution / 2.0).numpy()
+    idx_c, keep_c = c_oracle.voxel_indices(fr[0, 0, :, 0].numpy(), fr[0, :, 0, 1].numpy(), fr[:, 0, 0, 2].numpy(), comb, trans, off,
+                                           oracle.resolution.numpy(), oracle.dimension.numpy())
+    assert sha(idx_c) == golden_str(golden_lift[f"{tag}__idx_sha256"])
+    assert sha(keep_c) == golden_str(golden_lift[f"{tag}__keep_sha256"])
