@@ -12,13 +12,61 @@
 """
 from __future__ import annotations
 
+import functools
 import importlib
+import warnings
 
 from .geometry import VoxelsSumming
 from .lift import calculate_birds_eye_view_features
 from .warp import cumulative_warp_features, warp_features
 
 _saved = {}
+_warned = set()
+
+
+def unsupported_reason(model, x):
+    """None if the fused kernels cover this model's lift configuration, else the reason (the limits of
+    fiery_b200/csrc: include/fiery_b200.h).  CPU tensors are NOT a reason: there is no CPU path and the call raises."""
+    h, w = x.shape[-2] // model.encoder_downsample, x.shape[-1] // model.encoder_downsample
+    D = model.frustum.shape[0]
+    if int(model.encoder_out_channels) != 64:
+        return f"MODEL.ENCODER.OUT_CHANNELS={int(model.encoder_out_channels)} (kernels are built for 64)"
+    if D > 48:
+        return f"{D} depth bins (kernels are built for <= 48)"
+    if h > 32 or w % 4:
+        return f"feature map {h}x{w} (kernels need h <= 32 and w % 4 == 0)"
+    if int(model.bev_dimension[2]) != 1:
+        return "more than one height cell"
+    return None
+
+
+def _warn_once(key, msg):
+    if key not in _warned:
+        _warned.add(key)
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
+def _bev_features(self, x, intrinsics, extrinsics):
+    """Installed as ``Fiery.calculate_birds_eye_view_features``: the fused lift where the kernels cover the configuration,
+    the reference's own method (unpatched behaviour, its own device) where they do not."""
+    reason = unsupported_reason(self, x)
+    if reason is None:
+        return calculate_birds_eye_view_features(self, x, intrinsics, extrinsics)
+    _warn_once(("bev", reason), f"fiery_b200: lift configuration not covered by the CUDA kernels ({reason}); "
+                                "running the reference's own calculate_birds_eye_view_features")
+    return _saved["bev"](self, x, intrinsics, extrinsics)
+
+
+def _bilinear_only(ours, saved_key):
+    """Feature warps (mode='bilinear', fiery.py:143) run on the CUDA kernel.  The trainer's label warps use mode='nearest'
+    (trainer.py, cumulative_warp_features_reverse): sample positions agree with torch only to ~1e-4, which can flip a
+    nearest-neighbour pick at a tie, so those stay on the reference's function."""
+    @functools.wraps(ours)
+    def fn(x, flow, mode="nearest", spatial_extent=None):
+        if mode == "bilinear" or _saved.get(saved_key) is None:
+            return ours(x, flow, mode=mode, spatial_extent=spatial_extent)
+        return _saved[saved_key](x, flow, mode=mode, spatial_extent=spatial_extent)
+    return fn
 
 
 def install(level: str = "fused"):
@@ -35,11 +83,11 @@ def install(level: str = "fused"):
     geometry.VoxelsSumming = VoxelsSumming
     fiery_mod.VoxelsSumming = VoxelsSumming
     if level in ("fused", "all"):
-        fiery_mod.Fiery.calculate_birds_eye_view_features = calculate_birds_eye_view_features
+        fiery_mod.Fiery.calculate_birds_eye_view_features = _bev_features
     if level == "all":
-        geometry.cumulative_warp_features = cumulative_warp_features
-        geometry.warp_features = warp_features
-        fiery_mod.cumulative_warp_features = cumulative_warp_features
+        geometry.cumulative_warp_features = _bilinear_only(cumulative_warp_features, "cwf")
+        geometry.warp_features = _bilinear_only(warp_features, "wf")
+        fiery_mod.cumulative_warp_features = _bilinear_only(cumulative_warp_features, "cwf_model")
     return fiery_mod.Fiery
 
 
@@ -56,3 +104,4 @@ def uninstall():
         if _saved.get(key) is not None:
             setattr(mod, name, _saved[key])
     _saved.clear()
+    _warned.clear()

@@ -12,6 +12,7 @@ grid tensors, under the same names, so a reference ``state_dict`` loads into it 
 """
 from __future__ import annotations
 
+import collections
 import os
 from typing import Dict, Optional, Tuple
 
@@ -46,19 +47,33 @@ def unpack_sequence_dim(x: torch.Tensor, b: int, s: int) -> torch.Tensor:
 
 class _ScratchPool:
     """Zero-initialised accumulation buffers, one per (device, stream, size).  The kernels leave a buffer all-zero
-    again when they finish (include/fiery_b200.h), so it is allocated and cleared once."""
+    again when they finish (include/fiery_b200.h), so it is allocated and cleared once.  At most ``max_entries`` buffers
+    are kept (least recently used first out); a call that fails drops its buffer (``discard``), because a launch sequence that
+    stopped half way may have left it dirty."""
 
-    def __init__(self):
-        self._bufs: Dict[Tuple[int, int, int], torch.Tensor] = {}
+    def __init__(self, max_entries: int = 4):
+        self._bufs: "collections.OrderedDict[Tuple[int, int, int], torch.Tensor]" = collections.OrderedDict()
+        self.max_entries = max_entries
+
+    @staticmethod
+    def _key(device: torch.device, nbytes: int):
+        return (device.index if device.index is not None else torch.cuda.current_device(),
+                torch.cuda.current_stream(device).cuda_stream, nbytes)
 
     def get(self, device: torch.device, nbytes: int) -> torch.Tensor:
-        key = (device.index if device.index is not None else torch.cuda.current_device(),
-               torch.cuda.current_stream(device).cuda_stream, nbytes)
+        key = self._key(device, nbytes)
         buf = self._bufs.get(key)
         if buf is None:
             buf = torch.zeros(nbytes // 4, dtype=torch.float32, device=device)
             self._bufs[key] = buf
+            while len(self._bufs) > self.max_entries:
+                self._bufs.popitem(last=False)       # the evicted tensor is freed once its queued work has run (caching allocator)
+        else:
+            self._bufs.move_to_end(key)
         return buf
+
+    def discard(self, device: torch.device, nbytes: int) -> None:
+        self._bufs.pop(self._key(device, nbytes), None)
 
     def clear(self) -> None:
         self._bufs.clear()
@@ -105,13 +120,16 @@ class LiftSplat(nn.Module):
 
     @classmethod
     def from_fiery(cls, model, **kw) -> "LiftSplat":
-        """Adopts the constants of an instantiated reference ``Fiery`` module (shares nothing, copies values)."""
+        """Adopts the constants of an instantiated reference ``Fiery`` module.  The four Parameters are SHARED with the model
+        (same tensors), so a checkpoint loaded into the model afterwards, ``model.to(...)`` or an in-place edit is seen here:
+        the device-side constants are re-derived whenever the tensors' storage or version changes (``_param_key``)."""
         self = cls.__new__(cls)
         nn.Module.__init__(self)
-        self.bev_resolution = nn.Parameter(model.bev_resolution.detach().clone(), requires_grad=False)
-        self.bev_start_position = nn.Parameter(model.bev_start_position.detach().clone(), requires_grad=False)
-        self.bev_dimension = nn.Parameter(model.bev_dimension.detach().clone(), requires_grad=False)
-        self.frustum = nn.Parameter(model.frustum.detach().clone(), requires_grad=False)
+        as_param = lambda t: t if isinstance(t, nn.Parameter) else nn.Parameter(t, requires_grad=False)   # noqa: E731
+        self.bev_resolution = as_param(model.bev_resolution)
+        self.bev_start_position = as_param(model.bev_start_position)
+        self.bev_dimension = as_param(model.bev_dimension)
+        self.frustum = as_param(model.frustum)
         self.encoder_out_channels = int(model.encoder_out_channels)
         enc = getattr(model, "encoder", None)
         self.use_depth_distribution = bool(getattr(enc, "use_depth_distribution", True))
@@ -125,16 +143,22 @@ class LiftSplat(nn.Module):
         self._consts = None
         return super()._apply(fn, *a, **k)
 
+    def _param_key(self):
+        """Identity + in-place version of the four constant tensors: load_state_dict / .data edits / copy_ change it."""
+        return tuple((p.data_ptr(), p._version, str(p.device), tuple(p.shape))
+                     for p in (self.frustum, self.bev_resolution, self.bev_start_position, self.bev_dimension))
+
     def _constants(self, device: torch.device):
         c = self._consts
-        if c is not None and c["device"] == device:
+        key = self._param_key()
+        if c is not None and c["device"] == device and c["key"] == key:
             return c
         u, v, d = split_frustum(self.frustum)
         dim = [int(x) for x in self.bev_dimension.detach().cpu().tolist()]
         res = self.bev_resolution.detach().float().cpu().numpy().astype(np.float32)
         off = bev_offset_fp32(self.bev_start_position, self.bev_resolution)
         z_lo, z_hi = z_valid_interval(float(res[2]), dim[2])
-        c = dict(device=device, u=u.to(device), v=v.to(device), d=d.to(device), dim=dim, res=res, off=off,
+        c = dict(device=device, key=key, u=u.to(device), v=v.to(device), d=d.to(device), dim=dim, res=res, off=off,
                  z_lo=float(z_lo), z_hi=float(z_hi), D=int(d.numel()), h=int(v.numel()), w=int(u.numel()))
         self._consts = c
         return c
@@ -289,6 +313,7 @@ class LiftSplat(nn.Module):
         head = head.contiguous()
         mode, a, b = self._calibration(intrinsics.to(dev), extrinsics.to(dev))
         X, Y, _ = c["dim"]
+        pooled = 0
         with torch.cuda.device(dev):
             if self.output_layout == "channels_last":
                 desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NHWC)
@@ -299,11 +324,15 @@ class LiftSplat(nn.Module):
                 store = torch.empty((B, C, X, Y), dtype=torch.float32, device=dev)
                 out = store
                 if scratch is None and B:
-                    scratch = _scratch.get(dev, int(lib.fiery_lift_scratch_bytes(desc)))
+                    pooled = int(lib.fiery_lift_scratch_bytes(desc))
+                    scratch = _scratch.get(dev, pooled)
                 scratch_ptr = scratch.data_ptr() if B else 0
-            _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
-                                              c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
-                                              _stream_ptr(dev)), "fiery_lift_forward")
+            status = lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
+                                            c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
+                                            _stream_ptr(dev))
+            if status != 0 and pooled:
+                _scratch.discard(dev, pooled)          # a launch sequence that stopped half way may have left it dirty
+            _lib.check(status, "fiery_lift_forward")
         return out
 
     def _launch_backward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
@@ -403,7 +432,7 @@ def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):
     head = enc.depth_layer(enc.get_features(x.view(b * s * n, c, h, w)))          # encoder.py:94-96
     lift = getattr(self, "_fiery_b200_lift", None)
     if lift is None:
-        lift = LiftSplat.from_fiery(self).to(head.device)
+        lift = LiftSplat.from_fiery(self)          # shares the model's Parameters; device-side constants follow them
         object.__setattr__(self, "_fiery_b200_lift", lift)
     bev = lift(head, intrinsics, extrinsics)
     return unpack_sequence_dim(bev, b, s)

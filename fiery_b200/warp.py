@@ -4,65 +4,19 @@ Mirrors, same names / arguments / return values:
   * ``warp_features(x, flow, mode='nearest', spatial_extent=None)``              fiery/utils/geometry.py:181-222
   * ``cumulative_warp_features(x, flow, mode='nearest', spatial_extent=None)``   fiery/utils/geometry.py:225-253
     (call site fiery/models/fiery.py:143-146 with ``mode='bilinear'``)
-and the pose helpers they use (``pose_vec2mat`` :145-160, ``euler2mat`` :110-142, ``mat2pose_vec`` :82-107).
 
 Two launches per call through the C ABI (fiery_b200/csrc/warp.cu): ``warp_theta_kernel`` evaluates the 6-DoF pose algebra
-(one thread per sequence, a few 4x4 matrices) and ``warp_forward_kernel`` does the sampling -- ``affine_grid`` +
-``grid_sample`` over the (b, C, X, Y) feature maps, 10 MB per frame each way -- for all past frames of a sequence straight
-into the output tensor; the present frame is copied.  The pose helpers below are the torch restatements kept for users of
-those names (``pose_vec2mat`` etc. are public in the reference); the warps do not call them.  No CPU path.
+(``pose_vec2mat`` :145-160, ``euler2mat`` :110-142, the running product, ``mat2pose_vec`` :82-107; one thread per sequence, a
+few 4x4 matrices) and ``warp_forward_kernel`` does the sampling -- ``affine_grid`` + ``grid_sample`` over the (b, C, X, Y)
+feature maps, 10 MB per frame each way -- for all past frames of a sequence straight into the output tensor; the present
+frame is copied.  No CPU path.
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
 from .geometry import _require_cuda, _stream_ptr
-
-
-def euler2mat(angle: torch.Tensor) -> torch.Tensor:
-    """(..., 3) Euler angles -> (..., 3, 3) rotation = Rx @ Ry @ Rz; geometry.py:110-142."""
-    shape = angle.shape
-    a = angle.reshape(-1, 3)
-    x, y, z = a[:, 0], a[:, 1], a[:, 2]
-    zeros, ones = torch.zeros_like(z), torch.ones_like(z)
-    cosz, sinz = torch.cos(z), torch.sin(z)
-    zmat = torch.stack([cosz, -sinz, zeros, sinz, cosz, zeros, zeros, zeros, ones], dim=1).view(-1, 3, 3)
-    cosy, siny = torch.cos(y), torch.sin(y)
-    ymat = torch.stack([cosy, zeros, siny, zeros, ones, zeros, -siny, zeros, cosy], dim=1).view(-1, 3, 3)
-    cosx, sinx = torch.cos(x), torch.sin(x)
-    xmat = torch.stack([ones, zeros, zeros, zeros, cosx, -sinx, zeros, sinx, cosx], dim=1).view(-1, 3, 3)
-    return xmat.bmm(ymat).bmm(zmat).view(*shape[:-1], 3, 3)
-
-
-def pose_vec2mat(vec: torch.Tensor) -> torch.Tensor:
-    """(..., 6) (tx, ty, tz, rx, ry, rz) -> (..., 4, 4); geometry.py:145-160."""
-    rot_mat = euler2mat(vec[..., 3:].contiguous())
-    transform = torch.cat([rot_mat, vec[..., :3].unsqueeze(-1)], dim=-1)
-    transform = F.pad(transform, [0, 0, 0, 1], value=0)
-    transform[..., 3, 3] = 1.0
-    return transform
-
-
-def mat2pose_vec(matrix: torch.Tensor) -> torch.Tensor:
-    """(..., 4, 4) -> (..., 6); geometry.py:82-107."""
-    rotx = torch.atan2(-matrix[..., 1, 2], matrix[..., 2, 2])
-    cosy = torch.sqrt(matrix[..., 1, 2] ** 2 + matrix[..., 2, 2] ** 2)
-    roty = torch.atan2(matrix[..., 0, 2], cosy)
-    rotz = torch.atan2(-matrix[..., 0, 1], matrix[..., 0, 0])
-    return torch.cat((matrix[..., :3, 3], torch.stack((rotx, roty, rotz), dim=-1)), dim=-1)
-
-
-def _theta(flow: torch.Tensor, spatial_extent) -> torch.Tensor:
-    """The (b, 2, 3) affine map of warp_features: z-rotation + normalised xy translation; geometry.py:197-219."""
-    angle = flow[:, 5].clone()
-    translation = flow[:, :2].clone()
-    translation[:, 0] /= spatial_extent[0]
-    translation[:, 1] /= spatial_extent[1]
-    translation[:, 0] *= -1
-    cos_theta, sin_theta = torch.cos(angle), torch.sin(angle)
-    return torch.stack([cos_theta, -sin_theta, translation[:, 1], sin_theta, cos_theta, translation[:, 0]], dim=-1).view(-1, 2, 3)
 
 
 def _mode_flag(mode: str) -> int:
@@ -150,7 +104,14 @@ def cumulative_warp_features(x: torch.Tensor, flow: torch.Tensor, mode: str = "n
     if T == 1:
         return x
     _require_cuda(x, "x")
-    theta, copy_mask = _device_theta(flow[:, :T], spatial_extent, cumulative=True)
+    F_len = flow.shape[1]
+    if F_len < max(2, T - 1):
+        raise IndexError(f"flow has {F_len} timesteps, the sequence {T}: the reference indexes flow[:, -2] and flow[:, t - 1]")
+    if F_len != T:
+        # the reference starts the running product at flow[:, -2] of flow's OWN length and continues with flow[:, t - 1]
+        # indexed by the sequence's t (geometry.py:246-251): an effective per-frame sequence with that hybrid indexing
+        flow = torch.cat([flow[:, :T - 2], flow[:, F_len - 2:F_len - 1], flow[:, F_len - 1:F_len]], dim=1)
+    theta, copy_mask = _device_theta(flow, spatial_extent, cumulative=True)
     xm = x.reshape(b * T, *x.shape[2:])
     res = _WarpMaps.apply(xm, theta, copy_mask, _mode_flag(mode)).view(x.shape)
     return res if x.dtype == torch.float32 else res.to(x.dtype)

@@ -134,3 +134,32 @@ def test_shard_frames_partitions():
             parts = [list(shard_frames(n, ws, r)) for r in range(ws)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_constants_follow_checkpoint_loads_and_in_place_edits():
+    """The device-side constants are re-derived when the Parameters change under the module: ``load_state_dict`` copies in
+    place (no ``_apply``), and in the reference the checkpoint's values win (fiery/models/fiery.py:21-23 are Parameters)."""
+    import torch
+    from fiery_b200.lift import LiftSplat
+    a = LiftSplat(x_bound=(-50.0, 50.0, 0.5), y_bound=(-50.0, 50.0, 0.5))
+    b = LiftSplat(x_bound=(-40.0, 40.0, 0.5), y_bound=(-50.0, 50.0, 0.5))
+    cpu = torch.device("cpu")
+    before = a._constants(cpu)
+    assert before is a._constants(cpu)                            # cached while nothing changes
+    assert before["dim"][0] == 200 and abs(float(before["off"][0]) + 50.0) < 1e-6
+    a.load_state_dict(b.state_dict())
+    after = a._constants(cpu)
+    assert after is not before and after["dim"][0] == 160 and abs(float(after["off"][0]) + 40.0) < 1e-6
+    with torch.no_grad():
+        a.bev_start_position[1] += 1.0
+    assert abs(float(a._constants(cpu)["off"][1]) + 49.0) < 1e-6
+    # from_fiery shares the model's Parameters: a later edit of the model is seen
+    import types
+    model = types.SimpleNamespace(frustum=b.frustum, bev_resolution=b.bev_resolution, bev_start_position=b.bev_start_position,
+                                  bev_dimension=b.bev_dimension, encoder_out_channels=64)
+    shared = LiftSplat.from_fiery(model)
+    assert shared.frustum is b.frustum
+    x0 = float(shared._constants(cpu)["off"][0])
+    with torch.no_grad():
+        b.bev_start_position[0] -= 2.0
+    assert abs(float(shared._constants(cpu)["off"][0]) - (x0 - 2.0)) < 1e-6

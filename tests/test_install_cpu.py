@@ -53,13 +53,47 @@ def test_install_rebinds_and_uninstall_restores(fake_fiery):
     assert geometry.VoxelsSumming is ours and fiery_mod.VoxelsSumming is ours      # both bindings (fiery.py:10)
     assert fiery_mod.Fiery.calculate_birds_eye_view_features is ref_bev
     fb.install()                                                                    # level="fused"
-    assert fiery_mod.Fiery.calculate_birds_eye_view_features is ours_bev
+    assert fiery_mod.Fiery.calculate_birds_eye_view_features is fb._bev_features    # dispatches to ours_bev where supported
+    assert ours_bev.__name__ == "calculate_birds_eye_view_features"
     fb.install(level="all")
     from fiery_b200.warp import cumulative_warp_features as ours_cwf
-    assert fiery_mod.cumulative_warp_features is ours_cwf and geometry.cumulative_warp_features is ours_cwf
+    assert fiery_mod.cumulative_warp_features.__wrapped__ is ours_cwf and geometry.cumulative_warp_features.__wrapped__ is ours_cwf
+    # label warps (mode='nearest', the trainer's cumulative_warp_features_reverse) stay on the reference's function
+    assert fiery_mod.cumulative_warp_features("x", None, mode="nearest") == "reference"
+    assert geometry.warp_features("x", None, mode="nearest") == "reference"
     fb.uninstall()
-    assert fiery_mod.cumulative_warp_features is not ours_cwf and geometry.cumulative_warp_features("x", None) == "reference"
+    assert not hasattr(fiery_mod.cumulative_warp_features, "__wrapped__") and geometry.cumulative_warp_features("x", None) == "reference"
     assert geometry.VoxelsSumming is ref_vs and fiery_mod.VoxelsSumming is ref_vs
     assert fiery_mod.Fiery.calculate_birds_eye_view_features is ref_bev
     with pytest.raises(ValueError):
         fb.install(level="nope")
+
+
+def test_unsupported_configuration_runs_the_reference_method(fake_fiery):
+    """A lift configuration the kernels do not cover (e.g. MODEL.ENCODER.OUT_CHANNELS != 64, fiery/config.py:78) keeps the
+    reference's own method, with one warning; a covered one is routed to the fused lift (which raises on CPU tensors: there
+    is no CPU path)."""
+    import types
+    import torch
+    import fiery_b200.install as fb
+    from fiery_b200 import _lib
+    fiery_mod = importlib.import_module("fiery.models.fiery")
+    fb.install()
+    try:
+        m = fiery_mod.Fiery()
+        m.encoder_downsample, m.encoder_out_channels = 8, 32
+        m.frustum = torch.zeros(48, 28, 60, 3)
+        m.bev_dimension = torch.tensor([200, 200, 1])
+        x = torch.zeros(1, 1, 6, 3, 224, 480)
+        assert "OUT_CHANNELS" in fb.unsupported_reason(m, x)
+        with pytest.warns(RuntimeWarning, match="not covered"):
+            assert m.calculate_birds_eye_view_features(x, None, None) == "reference"
+        m.encoder_out_channels = 64
+        assert fb.unsupported_reason(m, x) is None
+        m.encoder = types.SimpleNamespace(get_features=lambda t: t[:, :, ::8, ::8], depth_layer=lambda t: t.repeat(1, 38, 1, 1)[:, :112],
+                                          use_depth_distribution=True)
+        m.bev_resolution, m.bev_start_position = torch.tensor([0.5, 0.5, 20.0]), torch.tensor([-49.75, -49.75, 0.0])
+        with pytest.raises(_lib.FieryError, match="no CPU path"):
+            m.calculate_birds_eye_view_features(x, torch.eye(3).expand(1, 1, 6, 3, 3), torch.eye(4).expand(1, 1, 6, 4, 4))
+    finally:
+        fb.uninstall()
