@@ -6,9 +6,13 @@
 One "step" = one pass of the hot path {head tensor, intrinsics, extrinsics} -> BEV (B', C, X, Y) over one batch of
 synthetic frames.  Prints ONE JSON line (rank 0).
 
-  value      whole-job frames/s, inputs resident in HBM, through the public Python API (LiftSplat.forward -> C ABI)
+  value      whole-job frames/s, inputs resident in HBM, through the public Python API (LiftSplat.capture -> C ABI): one step =
+             geometry plan + tile kernels + layout passes of the whole batch (nothing is cached between steps)
   e2e        same metric with HOST (pinned) inputs and a host copy of the BEV inside the timed region
-  roofline   the dominant kernel (lift_forward_cols_kernel) against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline   the PATH against the measured HBM copy bandwidth (MEASURED_PEAKS.json): algorithmic bytes of the step / step time;
+             `kernels` lists every kernel of the step with its OWN algorithmic bytes, the duration of the launches the step really
+             runs (event pairs on their streams, fiery_lift_forward_timed) and the ncu DRAM bytes of the committed capture
+  roofline_bwd  the same for the backward (grad of the head tensor)
   cpu_baseline  the oracle's torch-CPU restatement of the reference op chain on this box's host cores, bounded sample
 
 `--impl reference` times that CPU restatement itself (the reference is pure PyTorch; /root/reference is not on the GPU
@@ -38,14 +42,15 @@ L2_FLUSH_BYTES = 256 << 20
 
 
 def load_traffic(workload: str):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this workload (profiles/traffic.json)."""
+    """ncu DRAM bytes (read + write) per step of every kernel of this workload, from the committed captures
+    (profiles/traffic.json: {workload: {kernel: bytes per step}}); {} when there is no capture."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(path) as fh:
             v = json.load(fh).get(workload)
-        return int(v) if v is not None else None
+        return {k: int(b) for k, b in v.items()} if isinstance(v, dict) else {}
     except (OSError, ValueError):
-        return None
+        return {}
 
 
 def load_peaks():
@@ -146,18 +151,26 @@ def time_cpu_reference(cfg: LiftConfig, frames: int, reps: int, warmup: int = 1)
     return frames / sec, sec, threads
 
 
+def config_dict(cfg: LiftConfig, args, world: int):
+    """`config` of the JSON line: identical for both arms (the reference arm runs the same frames per step)."""
+    X, Y = cfg.bev_hw
+    return {"workload": cfg.name, "frames_per_step_per_gpu": cfg.frames, "n_cameras": cfg.n_cameras,
+            "final_dim": list(cfg.final_dim), "feat_hw": list(cfg.feat_hw), "depth_bins": cfg.depth_bins,
+            "channels": cfg.out_channels, "bev": [X, Y], "direction": "forward", "output_layout": args.layout,
+            "head_dtype": args.head_dtype}
+
+
 def run_reference(args, cfg: LiftConfig, rank: int):
     if rank != 0:
         return
-    frames = min(cfg.frames, 3)
+    frames = cfg.frames                       # the same batch the GPU arm lifts per step
     steps = max(1, args.steps)
     fps, sec, threads = time_cpu_reference(cfg, frames, reps=steps, warmup=max(1, min(args.warmup, 2)))
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg.name, "frames_per_step": frames, "n_cameras": cfg.n_cameras,
-                   "final_dim": list(cfg.final_dim), "bev": list(cfg.bev_hw), "direction": "forward"},
+        "config": config_dict(cfg, args, 1),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} reps of {frames} frame(s) of {cfg.name}, torch-CPU op chain of the reference "
                                    f"(oracle/lift_oracle.py), best of thread counts up to {os.cpu_count()}: {threads} threads"},
@@ -181,6 +194,7 @@ def main():
                     help="dtype of the head tensor: f32 (the metric's definition) or f16 (AMP heads, baseline.yml PRECISION 16: the "
                          "forward tile kernel reads the half-precision tensor itself; all arithmetic stays fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the VoxelsSumming / warp / reference-ops-on-GPU side measurements")
     ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per upload/lift/download pipeline stage in the e2e run")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--cpu-reps", type=int, default=5)
@@ -196,13 +210,18 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device: fiery_b200 has no CPU path")
+    import ctypes
     import torch.distributed as dist
-    from fiery_b200 import _lib
+    from fiery_b200 import _lib, hostmem
     from fiery_b200.geometry import _stream_ptr
     from fiery_b200.lift import LiftSplat
-    _lib.load()
+    lib = _lib.load()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # one process per GPU, bound to the cores of its GPU's NUMA node before any pinned buffer exists (e2e: 118 MB cross PCIe per step)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    n_gpu_node = max(1, sum(1 for i in range(torch.cuda.device_count()) if hostmem.gpu_numa_node(i) == hostmem.gpu_numa_node(local_rank)))
+    numa = hostmem.bind_to_gpu_numa(local_rank, local_rank, min(local_world, n_gpu_node))
     distributed = world > 1
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -220,17 +239,19 @@ def main():
         head_d = head_d.to(head_dtype)
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
     W, S = max(args.warmup, 3), max(args.steps, 1)
+    X, Y = cfg.bev_hw
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed_steps(step_fn, n_steps):
+    def timed_steps(step_fn, n_steps, do_flush=True):
         """Per-step CUDA events on the current stream; L2 flushed (256 MiB write) before each step, outside the events."""
         times = []
         for _ in range(n_steps):
-            flush.fill_(1.0)
+            if do_flush:
+                flush.fill_(1.0)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             step_fn()
@@ -240,47 +261,60 @@ def main():
         return times
 
     # ---- value: device-resident inputs through the public API ----------------------------------------------------------
-    # LiftSplat.capture() records the forward lift (TMA descriptors + the tile-kernel / layout-pass chains of every frame
-    # group, forked over internal streams) into a CUDA graph once; a step is one replay.  The eager call (LiftSplat.forward) is timed too and reported as value_eager.
+    # LiftSplat.capture() records the forward lift (TMA descriptors + the plan-kernel / tile-kernel / layout-pass chains of every
+    # frame group, forked over internal streams) into a CUDA graph once; a step is one replay and recomputes EVERYTHING of the path,
+    # the geometry plan included.  value_static_rig: the same with the plan cached (LiftSplat.capture(static_calibration=True), the
+    # inference case of a fixed camera rig) -- reported next to the value, never as the value.
     def step_eager():
         with torch.no_grad():
             return lift(head_d, K_d, E_d)
 
     graphed = lift.capture(head_d, K_d, E_d)
-
-    def step_device():
-        return graphed()
+    graphed_static = lift.capture(head_d, K_d, E_d, static_calibration=True)
 
     for _ in range(W):
-        step_device()
+        graphed()
+        graphed_static()
         step_eager()
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    t_dev = timed_steps(step_device, S)
+    t_dev = timed_steps(graphed, S)
     barrier()
+    t_dev_noflush = timed_steps(graphed, S, do_flush=False)
+    t_static = timed_steps(graphed_static, S)
     t_eager = timed_steps(step_eager, S)
     barrier()
 
     # ---- forward + backward through autograd (the training-step view of the same path) -----------------------------------
     gout_d = torch.from_numpy(make_grad_bev(cfg, seed=100 + rank)).to(dev)
+    gout_cl = gout_d.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)        # the same gradient, channels-last strides
     head_g = head_d.clone().requires_grad_(True)
 
-    def step_fwd_bwd():
+    def step_fwd_bwd(g=gout_d):
         head_g.grad = None
-        lift(head_g, K_d, E_d).backward(gout_d)
+        lift(head_g, K_d, E_d).backward(g)
+
+    plan_d = lift.plan(K_d, E_d)
+    head_f32 = head_d.float()
+
+    def step_bwd_only(g):
+        return lift._launch_backward(head_f32, K_d, E_d, g, plan=plan_d)
 
     for _ in range(3):
         step_fwd_bwd()
+        step_bwd_only(gout_d)
+        step_bwd_only(gout_cl)
     barrier()
     t_fb = timed_steps(step_fwd_bwd, S)
+    t_bwd = timed_steps(lambda: step_bwd_only(gout_d), S)
+    t_bwd_cl = timed_steps(lambda: step_bwd_only(gout_cl), S)
     barrier()
 
     # ---- e2e: pinned host inputs, host copy of the result, all inside the timed region ---------------------------------
     head_h = torch.from_numpy(head_np).to(head_dtype).pin_memory()
     K_h, E_h = torch.from_numpy(K).pin_memory(), torch.from_numpy(E).pin_memory()
-    X, Y = cfg.bev_hw
     out_h = torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32).pin_memory()
 
     def step_e2e():
@@ -294,38 +328,32 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline: the kernels of the step through the C ABI, events on their stream; NHWC mode runs lift_forward_cols_kernel alone ----
-    lib = _lib.load()
+    # ---- per-kernel durations of the launches the step really runs (event pairs on the chains' own streams) ----------------------
     c = lift._constants(dev)
     stream = _stream_ptr(dev)
-
-    def make_kernel_only(layout_code, out_tensor):
-        desc = lift._desc(c, frames, cfg.n_cameras, head_dtype, _lib.CALIB_RAW, layout_code)
-        scratch = torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
-
-        def run():
-            _lib.check(lib.fiery_lift_forward(desc, head_d.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(),
-                                              c["v"].data_ptr(), c["d"].data_ptr(), out_tensor.data_ptr(), scratch.data_ptr(),
-                                              stream), "fiery_lift_forward")
-        return run, scratch
-
-    launches_per_step = int(lib.fiery_lift_forward_launches(
-        lift._desc(c, frames, cfg.n_cameras, head_dtype, _lib.CALIB_RAW,
-                   _lib.BEV_NHWC if args.layout == "channels_last" else _lib.BEV_NCHW)))
-    out_nchw = torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
-    acc_nhwc = torch.zeros((frames, X, Y, cfg.out_channels), dtype=torch.float32, device=dev)
-    run_fused, _s1 = make_kernel_only(_lib.BEV_NCHW, out_nchw)
-    run_tiles, _s2 = make_kernel_only(_lib.BEV_NHWC, acc_nhwc)       # tile items only (accumulates; values irrelevant here)
-    for _ in range(3):
-        run_fused()
-        run_tiles()
-    t_both = timed_steps(run_fused, S)          # lift_forward_cols_kernel + finalize_tma_kernel chains (eager C-ABI call)
-    t_kernel = timed_steps(run_tiles, S)        # lift_forward_cols_kernel alone (channel-last target)
+    layout_code = _lib.BEV_NHWC if args.layout == "channels_last" else _lib.BEV_NCHW
+    desc = lift._desc(c, frames, cfg.n_cameras, head_dtype, _lib.CALIB_RAW, layout_code)
+    launches_per_step = int(lib.fiery_lift_forward_launches(desc, 0))
+    scratch = torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
+    out_buf = (torch.zeros((frames, X, Y, cfg.out_channels), dtype=torch.float32, device=dev) if layout_code == _lib.BEV_NHWC
+               else torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32, device=dev))
+    KIND = {0: "lift_plan_kernel", 1: "lift_forward_cols_kernel", 2: "finalize_tma_kernel"}
+    per_kind = {k: [] for k in KIND}
+    cap = 64
+    ms_arr, kind_arr, n_arr = (ctypes.c_float * cap)(), (ctypes.c_int32 * cap)(), ctypes.c_int32(0)
+    for it in range(3 + S):
+        flush.fill_(1.0)
+        _lib.check(lib.fiery_lift_forward_timed(desc, head_d.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(),
+                                                c["v"].data_ptr(), c["d"].data_ptr(), out_buf.data_ptr(), scratch.data_ptr(), None,
+                                                stream, cap, ms_arr, kind_arr, ctypes.byref(n_arr)), "fiery_lift_forward_timed")
+        if it >= 3:
+            for i in range(n_arr.value):
+                per_kind[int(kind_arr[i])].append(float(ms_arr[i]))
     barrier()
 
     # ---- the literal drop-in at fiery.py:261: VoxelsSumming on one frame's rank-sorted point features ------------------------
     vs_extra = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and not args.no_extras:
         from fiery_b200.geometry import VoxelsSumming
         with torch.no_grad():
             idx1, valid1, pillar1 = lift.point_indices(K_d[:1], E_d[:1])
@@ -345,8 +373,8 @@ def main():
 
     # ---- next row of the path: cumulative_warp_features on the lifted BEV (b=3 samples x s=3 steps) ---------
     warp_extra = None
-    if rank == 0:
-        from fiery_b200.warp import cumulative_warp_features
+    if rank == 0 and not args.no_extras:
+        from fiery_b200.warp import cumulative_warp_features, _device_theta
         from fiery_b200.synthetic import make_egomotion
         wb, ws = 3, 3
         xw = torch.randn(wb, ws, cfg.out_channels, X, Y, device=dev)
@@ -358,18 +386,13 @@ def main():
             t_w = timed_steps(lambda: cumulative_warp_features(xw, fl, mode="bilinear", spatial_extent=ext), S)
         w_bytes = 2 * xw.numel() * 4                                    # read every frame once + write every frame once
         w_ms = float(np.mean(t_w))
-        # the sampling kernel alone through the C ABI (theta precomputed, output preallocated)
-        from fiery_b200.warp import _device_theta
-        from fiery_b200 import _lib as L
-        lib = L.load()
         th_w, mask_w = _device_theta(fl, ext, cumulative=True)
         out_w = torch.empty_like(xw)
         chw = cfg.out_channels * X * Y
-        sp = torch.cuda.current_stream(dev).cuda_stream
 
         def warp_kernel_only():
-            L.check(lib.fiery_warp_features_forward(wb * ws, cfg.out_channels, X, Y, xw.data_ptr(), chw, th_w.data_ptr(),
-                                                    mask_w.data_ptr(), out_w.data_ptr(), chw, 0, sp), "warp")
+            _lib.check(lib.fiery_warp_features_forward(wb * ws, cfg.out_channels, X, Y, xw.data_ptr(), chw, th_w.data_ptr(),
+                                                       mask_w.data_ptr(), out_w.data_ptr(), chw, 0, stream), "warp")
         for _ in range(3):
             warp_kernel_only()
         wk_ms = float(np.mean(timed_steps(warp_kernel_only, S)))
@@ -396,64 +419,107 @@ def main():
         return float(t.item())
 
     ms_dev = reduce_max(float(np.mean(t_dev)))
+    ms_dev_noflush = reduce_max(float(np.mean(t_dev_noflush)))
+    ms_static = reduce_max(float(np.mean(t_static)))
     ms_eager = reduce_max(float(np.mean(t_eager)))
     ms_fb = reduce_max(float(np.mean(t_fb)))
+    ms_bwd = reduce_max(float(np.mean(t_bwd)))
+    ms_bwd_cl = reduce_max(float(np.mean(t_bwd_cl)))
     ms_e2e = reduce_max(float(np.mean(t_e2e)))
-    ms_kernel = reduce_max(float(np.mean(t_kernel)))
-    ms_both = reduce_max(float(np.mean(t_both)))
     total_frames = frames * world
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        alg_bytes = cfg.fwd_bytes_per_frame(head_itemsize=head_d.element_size()) * frames
-        achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+        gbs = lambda nbytes, ms: nbytes / (ms * 1e-3) / 1e9                     # noqa: E731
+        es = head_d.element_size()
+        alg_bytes = cfg.fwd_bytes_per_frame(head_itemsize=es) * frames
+        head_bytes = head_d.numel() * es
+        bev_bytes = frames * cfg.out_channels * X * Y * 4
+        # counts of the plan: runs / stream entries written by the plan kernel, pillars that receive a point (accumulator rows the tile
+        # kernels reduce into and the layout pass gathers)
+        ps = lift.plan_summary(plan_d, frames, cfg.n_cameras)
+        touched_rows = ps["touched_pillars"]
+        row_bytes = cfg.out_channels * 4
+        plan_out = 4 * (ps["runs"] + ps["stream_entries"])
+        own = {"lift_plan_kernel": plan_out + touched_rows,                                # run lists + stream lists + marks (not HBM-bound)
+               "lift_forward_cols_kernel": head_bytes + touched_rows * row_bytes,             # read head once, each touched row written once
+               "finalize_tma_kernel": 2 * touched_rows * row_bytes + bev_bytes}               # gather + re-zero touched rows, write the BEV
+        traffic = load_traffic(cfg.name) if args.head_dtype == "f32" else {}
+        kernels = []
+        for k, name in KIND.items():
+            if not per_kind[k]:
+                continue
+            n_launch = len(per_kind[k]) // S
+            mean_ms = float(np.mean(per_kind[k]))
+            kernels.append({"kernel": name, "launches_per_step": n_launch, "ms_per_launch": mean_ms,
+                            "algorithmic_bytes_per_launch": own[name] // max(1, n_launch),
+                            "achieved": gbs(own[name] / max(1, n_launch), mean_ms), "unit": "GB/s",
+                            "frac": gbs(own[name] / max(1, n_launch), mean_ms) / peak,
+                            "traffic_per_step": traffic.get(name)})
+        bwd_alg = cfg.bwd_bytes_per_frame(head_itemsize=4) * frames
         line = {
             "metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": S,
             "warmup": W, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
+            "value_no_l2_flush": total_frames / (ms_dev_noflush * 1e-3), "ms_per_step_no_l2_flush": ms_dev_noflush,
+            "value_static_rig": total_frames / (ms_static * 1e-3), "ms_per_step_static_rig": ms_static,
             "value_eager": total_frames / (ms_eager * 1e-3), "ms_per_step_eager": ms_eager,
             "fwd_bwd": {"value": total_frames / (ms_fb * 1e-3), "unit": "frames/s", "ms_per_step": ms_fb,
-                        "what": "LiftSplat.forward + autograd backward to the head tensor (eager)"},
-            "config": {"workload": cfg.name, "frames_per_step_per_gpu": frames, "n_cameras": cfg.n_cameras,
-                       "final_dim": list(cfg.final_dim), "feat_hw": list(cfg.feat_hw), "depth_bins": cfg.depth_bins,
-                       "channels": cfg.out_channels, "bev": [X, Y], "direction": "forward", "output_layout": args.layout,
-                       "head_dtype": args.head_dtype,
+                        "what": "LiftSplat.forward + autograd backward to the head tensor (eager; the plan is computed once and shared)"},
+            "config": {**config_dict(cfg, args, world),
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                        "l2": "flushed before every timed step (256 MiB write); step time = CUDA events around the step",
-                       "api": "value: LiftSplat.capture() CUDA-graph replay; value_eager: LiftSplat.forward; "
+                       "api": "value: LiftSplat.capture() CUDA-graph replay (plan + tile kernels + layout passes every step); "
+                              "value_static_rig: capture(static_calibration=True); value_eager: LiftSplat.forward; "
                               "e2e: LiftSplat.lift_from_host (pinned host in/out, 3-stream chunk pipeline)",
+                       "host": {"numa_node": numa[0], "cores_bound": numa[1], "note": numa[2]},
                        "timing": "mean over steps, max over ranks"},
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(head_h.numel() * head_h.element_size() + K_h.numel() * 4 + E_h.numel() * 4),
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},
-            # kernels of the timed `value` region: per step, one tile kernel (+ one layout pass) per frame group
+            # kernels of the timed `value` region: per step and frame group one plan kernel, one tile kernel (+ one layout pass)
             "gpu_launches": launches_per_step * S,
-            "roofline": {"bound": "hbm", "kernel": "lift_forward_cols_kernel", "achieved": achieved, "peak": peak,
-                         "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": load_traffic(cfg.name) if args.head_dtype == "f32" else None,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": ms_kernel, "lift_plus_finalize_ms": ms_both,
-                         "step_frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / peak},
+            "roofline": {"bound": "hbm", "kernel": "path: " + " + ".join(k["kernel"] for k in kernels),
+                         "achieved": gbs(alg_bytes, ms_dev), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": gbs(alg_bytes, ms_dev) / peak,
+                         "traffic": (sum(v for v in traffic.values()) if traffic else None),
+                         "algorithmic_bytes_per_step": alg_bytes, "step_ms": ms_dev,
+                         "frac_no_l2_flush": gbs(alg_bytes, ms_dev_noflush) / peak,
+                         "frac_static_rig": gbs(alg_bytes, ms_static) / peak,
+                         "touched_pillars": touched_rows, "kernels": kernels,
+                         "how": "frac = algorithmic bytes of the step (head read once + BEV written once, SURVEY.md 8d) / graph-replay "
+                                "step time / measured copy bandwidth; kernels[]: own algorithmic bytes (DESIGN.md section 4) / mean "
+                                "duration of the launches the step runs (chains overlap, so durations include contention)"},
+            "roofline_bwd": {"bound": "hbm", "kernel": "nchw_to_nhwc_kernel + lift_backward_kernel",
+                             "achieved": gbs(bwd_alg, ms_bwd), "peak": peak, "unit": "GB/s", "frac": gbs(bwd_alg, ms_bwd) / peak,
+                             "algorithmic_bytes_per_step": bwd_alg, "step_ms": ms_bwd,
+                             "channels_last_grad": {"kernel": "lift_backward_kernel", "step_ms": ms_bwd_cl,
+                                                    "achieved": gbs(bwd_alg, ms_bwd_cl), "frac": gbs(bwd_alg, ms_bwd_cl) / peak},
+                             "traffic": (load_traffic(cfg.name + "__bwd") or None),
+                             "how": "fiery_lift_backward with the forward's plan, eager C-ABI call, L2 flushed before every step; "
+                                    "algorithmic bytes = read grad BEV + read head + write grad head (SURVEY.md 8d)"},
             "clocks": clocks,
         }
         if vs_extra is not None:
             line["voxels_summing_dropin"] = vs_extra
         if warp_extra is not None:
-            peak_w, _ = load_peaks()
-            warp_extra["frac_of_hbm_peak"] = warp_extra["achieved_gbs"] / peak_w
+            warp_extra["frac_of_hbm_peak"] = warp_extra["achieved_gbs"] / peak
             line["next_row_cumulative_warp"] = warp_extra
         if not args.no_cpu_baseline:
-            # the reference's own op chain (torch library kernels: softmax, inverse, argsort, cumsum, index_put ...) on this
-            # GPU -- the GPU-vs-GPU comparison SURVEY.md section 8d asks for next to the CPU number; baseline only
-            from oracle import lift_oracle as O
-            o_gpu = O.LiftOracle.from_config(cfg).to(dev)
-            head_ref = head_d.float()                     # the reference's chain is timed on fp32 values
-            with torch.no_grad():
-                for _ in range(2):
-                    o_gpu.lift(head_ref, K_d, E_d)
-                t_ref_gpu = timed_steps(lambda: o_gpu.lift(head_ref, K_d, E_d), 5)
-            line["reference_ops_on_gpu"] = {"value": frames / (float(np.mean(t_ref_gpu)) * 1e-3), "unit": "frames/s",
-                                            "ms_per_step": float(np.mean(t_ref_gpu)),
-                                            "what": "oracle/lift_oracle.py (the reference's PyTorch op chain) on CUDA tensors, "
-                                                    "torch library kernels, same inputs, 5 steps"}
+            if not args.no_extras:
+                # the reference's own op chain (torch library kernels: softmax, inverse, argsort, cumsum, index_put ...) on this
+                # GPU -- the GPU-vs-GPU comparison SURVEY.md section 8d asks for next to the CPU number; baseline only
+                from oracle import lift_oracle as O
+                o_gpu = O.LiftOracle.from_config(cfg).to(dev)
+                head_ref = head_d.float()                     # the reference's chain is timed on fp32 values
+                with torch.no_grad():
+                    for _ in range(2):
+                        o_gpu.lift(head_ref, K_d, E_d)
+                    t_ref_gpu = timed_steps(lambda: o_gpu.lift(head_ref, K_d, E_d), 5)
+                line["reference_ops_on_gpu"] = {"value": frames / (float(np.mean(t_ref_gpu)) * 1e-3), "unit": "frames/s",
+                                                "ms_per_step": float(np.mean(t_ref_gpu)),
+                                                "what": "oracle/lift_oracle.py (the reference's PyTorch op chain) on CUDA tensors, "
+                                                        "torch library kernels, same inputs, 5 steps"}
             fps, sec, threads = time_cpu_reference(cfg, min(frames, args.cpu_frames), reps=args.cpu_reps)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_reps} reps of {min(frames, args.cpu_frames)} frame(s) of {cfg.name}: "

@@ -10,7 +10,7 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_uint8, c_void_p
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfiery_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 DTYPE_F32, DTYPE_F16 = 0, 1
 CALIB_RAW, CALIB_COMPOSED = 0, 1
@@ -38,13 +38,20 @@ class LiftDesc(ctypes.Structure):
 SIGNATURES = {
     "fiery_abi_version": (c_int32, []),
     "fiery_last_error": (c_char_p, []),
+    "fiery_lift_plan_bytes": (c_size_t, [POINTER(LiftDesc)]),
+    "fiery_lift_plan": (c_int32, [POINTER(LiftDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fiery_lift_scratch_bytes": (c_size_t, [POINTER(LiftDesc)]),
-    "fiery_lift_forward_launches": (c_int32, [POINTER(LiftDesc)]),
+    "fiery_lift_scratch_zeroed_bytes": (c_size_t, [POINTER(LiftDesc)]),
+    "fiery_lift_forward_launches": (c_int32, [POINTER(LiftDesc), c_int32]),
     "fiery_lift_forward": (c_int32, [POINTER(LiftDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     c_void_p, c_void_p, c_void_p]),
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fiery_lift_forward_timed": (c_int32, [POINTER(LiftDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_int32, POINTER(c_float), POINTER(c_int32),
+                                           POINTER(c_int32)]),
+    "fiery_lift_set_max_chunk_frames": (None, [c_int32]),
     "fiery_lift_workspace_bytes": (c_size_t, [POINTER(LiftDesc)]),
     "fiery_lift_backward": (c_int32, [POINTER(LiftDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fiery_lift_point_indices": (c_int32, [POINTER(LiftDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "fiery_compose_calibration": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

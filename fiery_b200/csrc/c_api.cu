@@ -3,7 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 
-#include "lift_tile.cuh"
+#include "lift_plan.cuh"
 
 namespace fiery {
 
@@ -135,10 +135,16 @@ int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels
 }
 
 // launchers defined next to their kernels
-int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch, cudaStream_t);
-int lift_chunk_frames(int n_frames, long long pillars, int channels);
-int lift_forward_launches(const LiftParams& P);
-int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, float* workspace, cudaStream_t);
+int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, void* scratch, const void* plan,
+                        cudaStream_t);
+int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, cudaStream_t stream);
+int lift_chunk_frames(const LiftParams& P);
+size_t lift_scratch_frame_bytes(const LiftParams& P, size_t* accum_bytes_out);
+void lift_set_max_chunk_frames(int n);
+void lift_set_timer(LaunchTimer* t);
+int lift_forward_launches(const LiftParams& P, int has_plan);
+size_t lift_backward_relayout_bytes(const LiftParams& P);
+int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, float* workspace, const void* plan, cudaStream_t);
 int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t);
 int launch_compose(int n, const float* K, const float* E, float* combined, float* translation, cudaStream_t);
 int launch_warp(int forward, int n_maps, int C, int H, int W, const float* a, long long a_stride, const float* theta,
@@ -172,7 +178,7 @@ static int make_params(const fiery_lift_desc_t* d, const float* calib_a, const f
     P.head_channels = d->channels + (P.use_depth ? d->depth_bins : 0);
     P.calib_mode = d->calib_mode;
     P.calib_a = calib_a; P.calib_b = calib_b; P.fu = fu; P.fv = fv; P.fd = fd;
-    P.accum = nullptr; P.touched = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr; P.head_f16 = nullptr;
+    P.accum = nullptr; P.plan_tiles = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr; P.head_f16 = nullptr;
     P.bev_layout = d->bev_layout;
     P.pillars = static_cast<long long>(d->bev_x) * d->bev_y;
     P.grid = make_grid_params(*d);
@@ -189,43 +195,107 @@ FIERY_API int fiery_abi_version(void) { return FIERY_B200_ABI_VERSION; }
 
 FIERY_API const char* fiery_last_error(void) { return g_last_error; }
 
-FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
-    if (!d || d->bev_layout != FIERY_BEV_NCHW || d->n_frames <= 0) return 0;
-    const long long per_frame = static_cast<long long>(d->bev_x) * d->bev_y;
-    const size_t pillars = static_cast<size_t>(lift_chunk_frames(d->n_frames, per_frame, d->channels)) * per_frame;   // one chunk of frames
-    return pillars * d->channels * sizeof(float) + ((pillars + 15) & ~static_cast<size_t>(15));   // accumulator + touched map
-}
-
-FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* d) {
-    if (!d || d->n_frames <= 0 || d->n_cameras < 1 || d->feat_w < 1) return 0;
-    LiftParams P = {};
-    P.n_frames = d->n_frames; P.n_cameras = d->n_cameras; P.C = d->channels;
+// shape-only parameters for the size queries (no pointers)
+static bool shape_params(const fiery_lift_desc_t* d, LiftParams& P) {
+    if (!d || d->n_frames < 0 || d->n_cameras < 1 || d->feat_w < 1 || d->bev_x < 1 || d->bev_y < 1) return false;
+    P = LiftParams{};
+    P.n_frames = d->n_frames; P.n_cameras = d->n_cameras; P.C = d->channels; P.D = d->depth_bins;
+    P.hh = d->feat_h; P.ww = d->feat_w;
     P.n_wtiles = (d->feat_w + WT - 1) / WT;
     P.bev_layout = d->bev_layout;
     P.pillars = static_cast<long long>(d->bev_x) * d->bev_y;
-    return lift_forward_launches(P);
+    return true;
+}
+
+FIERY_API size_t fiery_lift_plan_bytes(const fiery_lift_desc_t* d) {
+    LiftParams P;
+    if (!shape_params(d, P) || P.n_frames == 0) return 0;
+    return plan_bytes(P.n_frames, P.n_cameras, P.n_wtiles, P.pillars);
+}
+
+FIERY_API int fiery_lift_plan(const fiery_lift_desc_t* desc, const float* calib_a, const float* calib_b, const float* frustum_u,
+                              const float* frustum_v, const float* frustum_d, void* plan_out, void* stream) {
+    LiftParams P;
+    int rc = make_params(desc, calib_a, calib_b, frustum_u, frustum_v, frustum_d, P);
+    if (rc != FIERY_OK) return rc;
+    if (P.n_frames == 0) return FIERY_OK;
+    FIERY_REQUIRE(plan_out != nullptr, "plan_out is NULL");
+    const PlanView v = plan_view(plan_out, P.n_frames, P.n_cameras, P.n_wtiles, P.pillars, 0);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FIERY_CUDA_CHECK(cudaMemsetAsync(const_cast<unsigned char*>(v.touched), 0, static_cast<size_t>(P.n_frames) * P.pillars, st));
+    return launch_lift_plan(P, const_cast<unsigned char*>(v.tiles), const_cast<unsigned char*>(v.touched), st);
+}
+
+FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
+    LiftParams P;
+    if (!shape_params(d, P) || P.n_frames == 0) return 0;
+    const size_t chunk = static_cast<size_t>(lift_chunk_frames(P));
+    size_t accum_frame = 0;
+    const size_t frame = lift_scratch_frame_bytes(P, &accum_frame);
+    const size_t zeroed = (chunk * accum_frame + 127) & ~static_cast<size_t>(127);
+    return zeroed + chunk * (frame - accum_frame);
+}
+
+FIERY_API size_t fiery_lift_scratch_zeroed_bytes(const fiery_lift_desc_t* d) {
+    LiftParams P;
+    if (!shape_params(d, P) || P.n_frames == 0) return 0;
+    size_t accum_frame = 0;
+    lift_scratch_frame_bytes(P, &accum_frame);
+    return (static_cast<size_t>(lift_chunk_frames(P)) * accum_frame + 127) & ~static_cast<size_t>(127);
+}
+
+FIERY_API void fiery_lift_set_max_chunk_frames(int32_t n) { lift_set_max_chunk_frames(n); }
+
+FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* d, int32_t has_plan) {
+    LiftParams P;
+    if (!shape_params(d, P) || P.n_frames == 0) return 0;
+    return lift_forward_launches(P, has_plan ? 1 : 0);
 }
 
 FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* d) {
-    if (!d || d->bev_layout != FIERY_BEV_NCHW) return 0;
-    return static_cast<size_t>(d->n_frames) * d->bev_x * d->bev_y * d->channels * sizeof(float);
+    LiftParams P;
+    if (!shape_params(d, P) || P.n_frames == 0) return 0;
+    const size_t relayout = (lift_backward_relayout_bytes(P) + 127) & ~static_cast<size_t>(127);
+    return relayout + static_cast<size_t>(P.n_frames) * P.n_cameras * P.n_wtiles * PLAN_TILE_BYTES;
 }
 
 FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                        const float* frustum_u, const float* frustum_v, const float* frustum_d, float* bev_out,
-                       float* scratch, void* stream) {
+                       void* scratch, const void* plan, void* stream) {
     LiftParams P;
     int rc = make_params(desc, calib_a, calib_b, frustum_u, frustum_v, frustum_d, P);
     if (rc != FIERY_OK) return rc;
     if (P.n_frames == 0) return FIERY_OK;
     FIERY_REQUIRE(head && bev_out, "head / bev_out is NULL");
-    FIERY_REQUIRE(desc->bev_layout == FIERY_BEV_NHWC || scratch != nullptr, "NCHW output needs the zeroed scratch buffer");
-    return launch_lift_forward(P, head, desc->head_dtype, bev_out, scratch, static_cast<cudaStream_t>(stream));
+    return launch_lift_forward(P, head, desc->head_dtype, bev_out, scratch, plan, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_lift_forward_timed(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
+                                       const float* frustum_u, const float* frustum_v, const float* frustum_d, float* bev_out,
+                                       void* scratch, const void* plan, void* stream, int32_t max_launches, float* host_ms,
+                                       int32_t* host_kind, int32_t* host_n_launches) {
+    FIERY_REQUIRE(host_ms && host_kind && host_n_launches && max_launches >= 1, "timed forward: NULL output / no room");
+    LaunchTimer t;
+    t.cap = max_launches < LaunchTimer::MAX ? max_launches : LaunchTimer::MAX;
+    for (int i = 0; i < 2 * t.cap; ++i) FIERY_CUDA_CHECK(cudaEventCreate(&t.ev[i]));
+    lift_set_timer(&t);
+    const int rc = fiery_lift_forward(desc, head, calib_a, calib_b, frustum_u, frustum_v, frustum_d, bev_out, scratch, plan, stream);
+    lift_set_timer(nullptr);
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    *host_n_launches = t.n;
+    for (int i = 0; i < t.n && rc == FIERY_OK && e == cudaSuccess; ++i) {
+        host_kind[i] = t.kind[i];
+        e = cudaEventElapsedTime(&host_ms[i], t.ev[2 * i], t.ev[2 * i + 1]);
+    }
+    for (int i = 0; i < 2 * t.cap; ++i) cudaEventDestroy(t.ev[i]);
+    if (rc != FIERY_OK) return rc;
+    FIERY_CUDA_CHECK(e);
+    return FIERY_OK;
 }
 
 FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                         const float* frustum_u, const float* frustum_v, const float* frustum_d, const float* grad_bev,
-                        void* grad_head, float* workspace, void* stream) {
+                        void* grad_head, float* workspace, const void* plan, void* stream) {
     LiftParams P;
     int rc = make_params(desc, calib_a, calib_b, frustum_u, frustum_v, frustum_d, P);
     if (rc != FIERY_OK) return rc;
@@ -233,9 +303,9 @@ FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* hea
     FIERY_REQUIRE(head && grad_bev && grad_head, "head / grad_bev / grad_head is NULL");
     P.grad_bev = grad_bev;
     P.grad_head = static_cast<float*>(grad_head);
-    FIERY_REQUIRE(desc->bev_layout == FIERY_BEV_NHWC || workspace != nullptr,
-                  "NCHW grad_bev needs a workspace of fiery_lift_workspace_bytes()");
-    return launch_lift_backward(P, head, desc->head_dtype, workspace, static_cast<cudaStream_t>(stream));
+    FIERY_REQUIRE(workspace != nullptr || (desc->bev_layout == FIERY_BEV_NHWC && plan != nullptr),
+                  "backward needs the workspace of fiery_lift_workspace_bytes() (NCHW grad_bev re-layout and/or the geometry plan)");
+    return launch_lift_backward(P, head, desc->head_dtype, workspace, plan, static_cast<cudaStream_t>(stream));
 }
 
 FIERY_API int fiery_lift_point_indices(const fiery_lift_desc_t* desc, const float* calib_a, const float* calib_b,

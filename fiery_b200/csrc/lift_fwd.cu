@@ -4,7 +4,10 @@
 // Replaces, per call: Fiery.get_geometry (fiery/models/fiery.py:193-208), the tail of Encoder.forward
 // (fiery/models/encoder.py:98-102), and Fiery.projection_to_birds_eye_view incl. VoxelsSumming
 // (fiery/models/fiery.py:221-273, fiery/utils/geometry.py:283-314).
-#include "lift_tile.cuh"
+#include <atomic>
+#include <mutex>
+
+#include "lift_plan.cuh"
 
 namespace fiery {
 
@@ -14,12 +17,13 @@ namespace fiery {
 // independent 16-byte loads (its own two cache lines, so the sectors are fully used through L1), and the warp then writes one
 // channel of 32 consecutive pillars per store instruction -- a full 128-byte line.  Only ~1/3-1/2 of the pillars receive any
 // point, and the tile kernel marks those in a byte map: unmarked pillars are written as zeros without touching the
-// accumulator; marked rows and their marks are re-zeroed on the way (scratch invariant of include/fiery_b200.h).
+// accumulator; marked rows (and, when the marks live in the scratch, the marks) are re-zeroed on the way (scratch invariant of
+// include/fiery_b200.h).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 256;
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flags, float* __restrict__ bev,
-                     long long pillars, int blocks_per_frame) {
+                     long long pillars, int blocks_per_frame, int clear_marks) {
     constexpr int C = 64;
     const int frame = blockIdx.x / blocks_per_frame;
     const long long pl = static_cast<long long>(blockIdx.x % blocks_per_frame) * FIN_THREADS + threadIdx.x;
@@ -32,7 +36,7 @@ finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flag
         for (int q = 0; q < C / 4; ++q) v[q] = row[q];
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) row[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        *f = 0;
+        if (clear_marks) *f = 0;
     } else {
 #pragma unroll
         for (int q = 0; q < C / 4; ++q) v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -79,7 +83,7 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 
 __global__ void __launch_bounds__(FT_THREADS)
 finalize_tma_kernel(const __grid_constant__ CUtensorMap bev_map, float* __restrict__ accum, unsigned char* __restrict__ touched,
-                    long long pillars, int tiles_per_frame, int frame_out0) {
+                    long long pillars, int tiles_per_frame, int frame_out0, int clear_marks) {
     constexpr int C = 64;
     __shared__ __align__(128) float s_in[FT_P * C];      // [pillar][channel]: bulk-copy destination
     __shared__ __align__(128) float s_out[C * FT_P];     // [channel][pillar]: TMA store source
@@ -142,7 +146,7 @@ finalize_tma_kernel(const __grid_constant__ CUtensorMap bev_map, float* __restri
     if (tid == 0) tma_store_3d(&bev_map, s_out, static_cast<int>(p0), 0, frame_out0 + frame);
     if (row) {                                          // restore the all-zero scratch
         bulk_store_1d(row, s_zero, C * 4);
-        *mark = 0;
+        if (clear_marks) *mark = 0;             // marks of a caller-owned plan stay: the plan is reused
     }
     if (tid == 0 || row) tma_store_commit_and_wait();   // the shared sources must outlive the copies
 }
@@ -191,47 +195,93 @@ __global__ void compose_calibration_kernel(int n, const float* __restrict__ K, c
 // ---------------------------------------------------------------------------------------------------------------------
 // host launchers (called from c_api.cu)
 // ---------------------------------------------------------------------------------------------------------------------
-// Frames per launch for NCHW output.  Measured on B200 (profiles/r01_notes.md): chunks small enough to keep the accumulator
-// L2-resident (3 frames, 31 MB) are slower end to end (152.9 us vs 122.7 us for 9 frames) -- the extra launches and the
-// single-wave grids cost more than the saved HBM traffic -- so the chunk only bounds the scratch footprint (1 GiB).
-int lift_chunk_frames(int n_frames, long long pillars, int channels) {
-    const long long per_frame = pillars * channels * 4 + pillars;
+// Frames per launch.  Measured on B200 (profiles/r01_notes.md): chunks small enough to keep the accumulator L2-resident (3 frames,
+// 31 MB) are slower end to end (152.9 us vs 122.7 us for 9 frames) -- the extra launches and the single-wave grids cost more than the
+// saved HBM traffic -- so the chunk only bounds the scratch footprint (1 GiB: accumulator + marks + plan records of a chunk).
+static std::atomic<int> g_max_chunk_frames{0};       // fiery_lift_set_max_chunk_frames (test hook: forces the multi-chunk path)
+void lift_set_max_chunk_frames(int n) { g_max_chunk_frames.store(n > 0 ? n : 0); }
+
+size_t lift_scratch_frame_bytes(const LiftParams& P, size_t* accum_bytes_out) {
+    const size_t tiles = static_cast<size_t>(P.n_cameras) * P.n_wtiles * PLAN_TILE_BYTES;
+    const size_t accum = P.bev_layout == FIERY_BEV_NCHW ? static_cast<size_t>(P.pillars) * P.C * 4 + static_cast<size_t>(P.pillars) : 0;
+    if (accum_bytes_out) *accum_bytes_out = accum;
+    return accum + tiles;
+}
+
+int lift_chunk_frames(const LiftParams& P) {
+    const long long per_frame = static_cast<long long>(lift_scratch_frame_bytes(P, nullptr));
     long long c = (1ll << 30) / (per_frame > 0 ? per_frame : 1);
-#ifdef FIERY_COLS_AB
-    if (const char* e = getenv("FIERY_CHUNK_FRAMES")) c = atoi(e);   // experiment builds: force the multi-chunk path on small batches
-#endif
-    if (c < 1) c = 1;
-    if (c > n_frames) c = n_frames;
+    const int forced = g_max_chunk_frames.load();
+    if (forced > 0 && forced < c) c = forced;
+    if (c > P.n_frames) c = P.n_frames;
     return static_cast<int>(c < 1 ? 1 : c);
 }
 
+// scratch of one chunk: [accumulator (chunk, X*Y, C) fp32][marks (chunk, X*Y) bytes, padded to 128][plan tile records of the chunk]
+struct ScratchParts {
+    float* accum;
+    unsigned char* marks;
+    unsigned char* tiles;
+    size_t zeroed_bytes, total_bytes;
+};
+ScratchParts lift_scratch_parts(const LiftParams& P, void* scratch, int chunk) {
+    ScratchParts s;
+    const bool nchw = P.bev_layout == FIERY_BEV_NCHW;
+    const size_t acc = nchw ? static_cast<size_t>(chunk) * P.pillars * P.C * 4 : 0;
+    const size_t marks = nchw ? ((static_cast<size_t>(chunk) * P.pillars + 127) & ~static_cast<size_t>(127)) : 0;
+    unsigned char* base = static_cast<unsigned char*>(scratch);
+    s.accum = reinterpret_cast<float*>(base);
+    s.marks = base + acc;
+    s.tiles = base + acc + marks;
+    s.zeroed_bytes = acc + marks;
+    s.total_bytes = acc + marks + static_cast<size_t>(chunk) * P.n_cameras * P.n_wtiles * PLAN_TILE_BYTES;
+    return s;
+}
+
 int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stream);
+int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, cudaStream_t stream);
 int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels, int n_frames, int box_pillars);
 
-// Side streams of the forward chains, created once per device (non-blocking).  Concurrent callers may share them: every call
-// orders its work with its own events, so sharing only serialises.
+// Side streams and fork/join events of the forward chains: created once per host thread and device (thread_local, so concurrent
+// callers never share or race on them), reused by every call -- nothing is created or destroyed on the launch path.
 constexpr int MAX_CHAINS = 4;
-static int side_streams(int n, cudaStream_t* out) {
-    static cudaStream_t pool[16][MAX_CHAINS - 1] = {};
+struct ChainResources {
+    cudaStream_t side[MAX_CHAINS - 1] = {};
+    cudaEvent_t fork = nullptr;
+    cudaEvent_t done[MAX_CHAINS - 1] = {};
+    bool ready = false;
+};
+static int chain_resources(ChainResources** out) {
+    static thread_local ChainResources pool[16];
     int dev = 0;
     FIERY_CUDA_CHECK(cudaGetDevice(&dev));
-    FIERY_REQUIRE(dev >= 0 && dev < 16 && n <= MAX_CHAINS - 1, "side streams: device %d / n=%d out of range", dev, n);
-    for (int i = 0; i < n; ++i) {
-        if (!pool[dev][i]) FIERY_CUDA_CHECK(cudaStreamCreateWithFlags(&pool[dev][i], cudaStreamNonBlocking));
-        out[i] = pool[dev][i];
+    FIERY_REQUIRE(dev >= 0 && dev < 16, "device %d out of range for the chain resources", dev);
+    ChainResources& r = pool[dev];
+    if (!r.ready) {
+        for (int i = 0; i < MAX_CHAINS - 1; ++i) {
+            FIERY_CUDA_CHECK(cudaStreamCreateWithFlags(&r.side[i], cudaStreamNonBlocking));
+            FIERY_CUDA_CHECK(cudaEventCreateWithFlags(&r.done[i], cudaEventDisableTiming));
+        }
+        FIERY_CUDA_CHECK(cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming));
+        r.ready = true;
     }
+    *out = &r;
     return FIERY_OK;
 }
 
-// NCHW output: the frames of a chunk are cut into groups, each a (tile kernel -> layout pass) chain on its own stream.  The
-// layout pass of one group (DRAM-bound) runs under the tile kernels of the others (issue-bound); only the last pass is
+// NCHW output: the frames of a chunk are cut into groups, each a (plan kernel ->) tile kernel -> layout pass chain on its own stream.
+// The layout pass of one group (DRAM-bound) runs under the tile kernels of the others (issue-bound); only the last pass is
 // exposed.  Measured on B200 (profiles/r01_notes.md), 8 frames: 1 chain 84.7 us, 2 chains 78.3 us, 4 chains 73.3 us; 8 chains of
-// one frame (90 tiles) each fall back to 79.6 us, so a group keeps at least one tile per SM (148).  A shorter last group (its
-// pass is the exposed one) does not help (137 -> 141 us at 400x200), and the same split of the backward (re-layout -> tile
-// kernel) gained nothing (159.2 -> 158.3 us); neither is done.
+// one frame (90 tiles) each fall back to 79.6 us, so a group keeps at least one tile per SM (148).
+#ifdef FIERY_COLS_AB
 static int g_max_chains = MAX_CHAINS;      // FIERY_CHAINS (A/B builds)
 static int g_chain_min_tiles = 148;        // FIERY_CHAIN_MIN_TILES (A/B builds)
+#else
+constexpr int g_max_chains = MAX_CHAINS;
+constexpr int g_chain_min_tiles = 148;
+#endif
 int lift_forward_groups(const LiftParams& P, int frames_in_chunk) {
+    if (P.bev_layout == FIERY_BEV_NHWC) return 1;          // no layout pass to hide
     int groups = frames_in_chunk < g_max_chains ? frames_in_chunk : g_max_chains;
     const long long tiles_per_frame = static_cast<long long>(P.n_cameras) * P.n_wtiles;
     while (groups > 1 && (frames_in_chunk / groups) * tiles_per_frame < g_chain_min_tiles) --groups;
@@ -239,86 +289,119 @@ int lift_forward_groups(const LiftParams& P, int frames_in_chunk) {
 }
 
 // kernel launches of one forward call (include/fiery_b200.h: fiery_lift_forward_launches)
-int lift_forward_launches(const LiftParams& P) {
+int lift_forward_launches(const LiftParams& P, int has_plan) {
     if (P.n_frames <= 0) return 0;
-    if (P.bev_layout == FIERY_BEV_NHWC) return 1;
-    const int chunk = lift_chunk_frames(P.n_frames, P.pillars, P.C);
+    const int per_group = (has_plan ? 0 : 1) + 1 + (P.bev_layout == FIERY_BEV_NCHW ? 1 : 0);
+    const int chunk = lift_chunk_frames(P);
     int n = 0;
     for (int f0 = 0; f0 < P.n_frames; f0 += chunk)
-        n += 2 * lift_forward_groups(P, (P.n_frames - f0 < chunk) ? P.n_frames - f0 : chunk);
+        n += per_group * lift_forward_groups(P, (P.n_frames - f0 < chunk) ? P.n_frames - f0 : chunk);
     return n;
 }
 
-int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, float* scratch,
+// Per-launch timing (bench / profiling): when set, every kernel launch of the next forward call on this host thread is bracketed by
+// a pair of events on its own stream; see fiery_lift_forward_timed in c_api.cu.
+static thread_local LaunchTimer* g_timer = nullptr;
+void lift_set_timer(LaunchTimer* t) { g_timer = t; }
+static inline void timer_begin(cudaStream_t st, int kind) {
+    if (g_timer && g_timer->n < g_timer->cap) {
+        g_timer->kind[g_timer->n] = kind;
+        cudaEventRecord(g_timer->ev[2 * g_timer->n], st);
+    }
+}
+static inline void timer_end(cudaStream_t st) {
+    if (g_timer && g_timer->n < g_timer->cap) {
+        cudaEventRecord(g_timer->ev[2 * g_timer->n + 1], st);
+        ++g_timer->n;
+    }
+}
+
+int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, void* scratch, const void* plan,
                         cudaStream_t stream) {
     FIERY_REQUIRE(head_dtype == FIERY_DTYPE_F32 || head_dtype == FIERY_DTYPE_F16, "head dtype %d not supported (fp32 / fp16)", head_dtype);
     FIERY_REQUIRE(P.C == 64, "channels=%d not supported by this build (C must be 64)", P.C);
     FIERY_REQUIRE(P.D >= 1 && P.D <= 48, "depth_bins=%d not supported by this build (1..48)", P.D);
     FIERY_REQUIRE(P.ww % 4 == 0, "feat_w=%d must be a multiple of 4 (TMA row pitch must be 16-byte aligned)", P.ww);
+    FIERY_REQUIRE(P.hh <= PLAN_MAX_ROWS, "feat_h=%d not supported by this build (<= %d)", P.hh, PLAN_MAX_ROWS);
+    const bool nchw = P.bev_layout == FIERY_BEV_NCHW;
+    FIERY_REQUIRE(scratch != nullptr || (!nchw && plan != nullptr), "the scratch buffer of fiery_lift_scratch_bytes() is required");
     int rc = FIERY_OK;
     LiftParams Q = P;
     Q.head_f16 = head_dtype == FIERY_DTYPE_F16 ? head : nullptr;
-    if (P.bev_layout == FIERY_BEV_NHWC) {          // the caller's zero-filled channel-last tensor is the accumulator
-        Q.accum = bev_out;
-        Q.touched = nullptr;
-        Q.frame0 = 0;
-        return launch_forward_cols(Q, head, stream);
-    }
 #ifdef FIERY_COLS_AB
     if (const char* e = getenv("FIERY_CHAINS")) g_max_chains = atoi(e) < MAX_CHAINS ? atoi(e) : MAX_CHAINS;
     if (const char* e = getenv("FIERY_CHAIN_MIN_TILES")) g_chain_min_tiles = atoi(e);
 #endif
-    // NCHW: lift into the channel-last accumulator, then the layout pass; chunked only to bound the scratch footprint
-    const int chunk = lift_chunk_frames(P.n_frames, P.pillars, P.C);
-    float* accum = scratch;                        // [accumulator floats of one chunk][one "touched" byte per pillar]
-    unsigned char* touched = reinterpret_cast<unsigned char*>(scratch + static_cast<size_t>(chunk) * P.pillars * P.C);
+    // lift into a channel-last accumulator (NHWC: the caller's zero-filled output itself), then the layout pass for NCHW; chunked
+    // only to bound the scratch footprint
+    const int chunk = lift_chunk_frames(P);
+    const ScratchParts sp = lift_scratch_parts(P, scratch, chunk);
+    const size_t tiles_per_frame = static_cast<size_t>(P.n_cameras) * P.n_wtiles;
     const bool tma_pass = P.pillars % 4 == 0;      // the output map needs a 16-byte row pitch
     CUtensorMap bev_map;
-    if (tma_pass) {
+    if (nchw && tma_pass) {
         rc = encode_bev_map(&bev_map, bev_out, P.pillars, P.C, P.n_frames, FT_P);
         if (rc != FIERY_OK) return rc;
     }
+    ChainResources* res = nullptr;
     for (int f0 = 0; f0 < P.n_frames; f0 += chunk) {
         const int nf = (P.n_frames - f0 < chunk) ? P.n_frames - f0 : chunk;
         const int groups = lift_forward_groups(P, nf);
         cudaStream_t chain[MAX_CHAINS] = {stream};
-        cudaEvent_t fork = nullptr;
         if (groups > 1) {                           // fork: the side streams start behind everything queued on the caller's
-            rc = side_streams(groups - 1, chain + 1);
-            if (rc != FIERY_OK) return rc;
-            FIERY_CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-            FIERY_CUDA_CHECK(cudaEventRecord(fork, stream));
+            if (!res) {
+                rc = chain_resources(&res);
+                if (rc != FIERY_OK) return rc;
+            }
+            for (int g = 1; g < groups; ++g) chain[g] = res->side[g - 1];
+            FIERY_CUDA_CHECK(cudaEventRecord(res->fork, stream));
         }
         for (int g = 0; g < groups; ++g) {
             const int s0 = static_cast<int>(static_cast<long long>(nf) * g / groups);
             const int s1 = static_cast<int>(static_cast<long long>(nf) * (g + 1) / groups);
             cudaStream_t st = chain[g];
-            if (g > 0) FIERY_CUDA_CHECK(cudaStreamWaitEvent(st, fork, 0));
+            if (g > 0) FIERY_CUDA_CHECK(cudaStreamWaitEvent(st, res->fork, 0));
             Q.frame0 = f0 + s0;
             Q.n_frames = s1 - s0;
-            Q.accum = accum + static_cast<size_t>(s0) * P.pillars * P.C;
-            Q.touched = touched + static_cast<size_t>(s0) * P.pillars;
-            rc = launch_forward_cols(Q, head, st);
-            if (rc != FIERY_OK) return rc;
-            if (tma_pass) {
-                const int tpf = static_cast<int>((P.pillars + FT_P - 1) / FT_P);
-                finalize_tma_kernel<<<static_cast<unsigned>(tpf) * Q.n_frames, FT_THREADS, 0, st>>>(bev_map, Q.accum, Q.touched,
-                                                                                                 P.pillars, tpf, Q.frame0);
-            } else {
-                const int bpf = static_cast<int>((P.pillars + FIN_THREADS - 1) / FIN_THREADS);
-                finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * Q.n_frames, FIN_THREADS, 0, st>>>(
-                    Q.accum, Q.touched, bev_out + static_cast<size_t>(Q.frame0) * P.C * P.pillars, P.pillars, bpf);
+            unsigned char* marks = nullptr;         // "pillar receives a point" bytes the layout pass reads
+            if (plan) {                             // caller-owned plan of the whole batch: read only
+                const PlanView v = plan_view(plan, P.n_frames, P.n_cameras, P.n_wtiles, P.pillars, Q.frame0);
+                Q.plan_tiles = v.tiles;
+                marks = const_cast<unsigned char*>(v.touched);
+            } else {                                // geometry of this group, into the scratch
+                unsigned char* tiles = sp.tiles + static_cast<size_t>(s0) * tiles_per_frame * PLAN_TILE_BYTES;
+                marks = nchw ? sp.marks + static_cast<size_t>(s0) * P.pillars : nullptr;
+                timer_begin(st, 0);
+                rc = launch_lift_plan(Q, tiles, marks, st);
+                timer_end(st);
+                if (rc != FIERY_OK) return rc;
+                Q.plan_tiles = tiles;
             }
-            FIERY_CUDA_CHECK(cudaGetLastError());
+            Q.accum = nchw ? sp.accum + static_cast<size_t>(s0) * P.pillars * P.C
+                           : bev_out + static_cast<size_t>(Q.frame0) * P.pillars * P.C;
+            timer_begin(st, 1);
+            rc = launch_forward_cols(Q, head, st);
+            timer_end(st);
+            if (rc != FIERY_OK) return rc;
+            if (nchw) {
+                timer_begin(st, 2);
+                if (tma_pass) {
+                    const int tpf = static_cast<int>((P.pillars + FT_P - 1) / FT_P);
+                    finalize_tma_kernel<<<static_cast<unsigned>(tpf) * Q.n_frames, FT_THREADS, 0, st>>>(bev_map, Q.accum, marks, P.pillars,
+                                                                                                     tpf, Q.frame0, plan ? 0 : 1);
+                } else {
+                    const int bpf = static_cast<int>((P.pillars + FIN_THREADS - 1) / FIN_THREADS);
+                    finalize_nchw_kernel<<<static_cast<unsigned>(bpf) * Q.n_frames, FIN_THREADS, 0, st>>>(
+                        Q.accum, marks, bev_out + static_cast<size_t>(Q.frame0) * P.C * P.pillars, P.pillars, bpf, plan ? 0 : 1);
+                }
+                timer_end(st);
+                FIERY_CUDA_CHECK(cudaGetLastError());
+            }
             if (g > 0) {                            // join the chain back into the caller's stream
-                cudaEvent_t done;
-                FIERY_CUDA_CHECK(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-                FIERY_CUDA_CHECK(cudaEventRecord(done, st));
-                FIERY_CUDA_CHECK(cudaStreamWaitEvent(stream, done, 0));
-                FIERY_CUDA_CHECK(cudaEventDestroy(done));           // released once the work it marks has completed
+                FIERY_CUDA_CHECK(cudaEventRecord(res->done[g - 1], st));
+                FIERY_CUDA_CHECK(cudaStreamWaitEvent(stream, res->done[g - 1], 0));
             }
         }
-        if (fork) FIERY_CUDA_CHECK(cudaEventDestroy(fork));
     }
     return FIERY_OK;
 }

@@ -1,9 +1,10 @@
-// Forward lift, the tile kernel: geometry + depth softmax + depth x context outer product + pillar pooling in one kernel; the
-// frustum volume (124 MB/frame in the reference, fiery/models/encoder.py:100) never leaves the SM.
+// Forward lift, the tile kernel: depth softmax + depth x context outer product + pillar pooling in one kernel; the frustum volume
+// (124 MB/frame in the reference, fiery/models/encoder.py:100) never leaves the SM.
 //
-// get_geometry (fiery.py:193-208), depth softmax x context outer product (encoder.py:98-100) and the voxel pooling of
-// projection_to_birds_eye_view (fiery.py:221-273) for one tile = one camera image x 4 feature columns x all rows x all depths x
-// all channels.
+// Depth softmax x context outer product (encoder.py:98-100) and the voxel pooling of projection_to_birds_eye_view
+// (fiery.py:221-273) for one tile = one camera image x 4 feature columns x all rows x all depths x all channels.  WHERE every
+// point lands (get_geometry fiery.py:193-208, indices / mask / ranks fiery.py:236-256) comes from the geometry plan
+// (lift_plan.cu), computed once per batch of calibrations and shared with the backward kernel.
 //
 // Observation the kernel is built on: at fixed (camera, column, depth) the h image rows of a column fall into one BEV pillar,
 // or a handful, because Z is collapsed (Z_BOUND has one cell) and cameras are close to level.  So the reference's global
@@ -19,12 +20,12 @@
 //     "4 adjacent columns of one (row, depth)" or "... of one (row, channel)";
 //   * a thread owns 2 depths x 4 columns x CPL channels, held as packed pairs of ADJACENT COLUMNS, so the outer product is
 //     4*CPL FFMA2 per row whose operands are exactly the register pairs the loads return;
-//   * the geometry (pillar of every point, reduced on the fly to run-end events) is evaluated while the TMA is in flight;
+//   * the tile's pillar runs are read from the plan and expanded into run-end events while the TMA is in flight;
 //   * the softmax runs in place on prob (lane = (depth mod 8, column): conflict free, reductions by shuffle);
 //   * run ends are detected warp-uniformly (one 32-bit load + one warp reduction per row, fetched a row ahead).
 #include <string.h>
 
-#include "lift_tile.cuh"
+#include "lift_plan.cuh"
 
 namespace fiery {
 
@@ -42,16 +43,11 @@ struct HeadMapsCols {
 
 struct ColsLayout {
     int hh, C;
-    int off_bar, off_cam, off_u, off_v, off_d, off_ev, off_prob, off_ctx, off_pillar, total;
+    int off_bar, off_ev, off_prob, off_ctx, off_pillar, total;
     __host__ __device__ ColsLayout(int hh_, int C_, int n_units) : hh(hh_), C(C_) {
         int o = 0;
         off_bar = o;    o += 16;
-        off_cam = o;    o += 12 * 4;
-        off_u = o;      o += WT * 4;
-        off_v = o;      o += 32 * 4;
-        off_d = o;      o += COLS_DPAD * 4;
-        o = (o + 15) & ~15;
-        off_ev = o;     o += n_units * COLS_EVS * 4;   // run-end events: [unit][row], see stage_geometry_cols
+        off_ev = o;     o += n_units * COLS_EVS * 4;   // run-end events: [unit][row], see expand_plan
         o = (o + 127) & ~127;
         off_prob = o;   o += hh * COLS_DPAD * WT * 4;
         o = (o + 127) & ~127;
@@ -90,147 +86,36 @@ __device__ __forceinline__ void clear_half(unsigned long long& v, unsigned keep)
     v &= HALF ? ((static_cast<unsigned long long>(keep) << 32) | 0xffffffffull) : (0xffffffff00000000ull | keep);
 }
 
-// ---- packed fp32x2 arithmetic for the geometry of TWO rows at a time (experiment builds, FIERY_COLS_AB) ------------------------
-// ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (and even fma(p, 1, c)), which would break the reference's separate
-// roundings; a chain of scalar FMUL feeding packed FADD2 survives (checked in SASS): products are formed per row with
-// __fmul_rn, everything additive runs packed.  add.rn.f32x2 / mul.rn.f32x2 round each half like the scalar instruction.
-__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-
-// pillars (rank or -1) of rows (v0, v1) of one (column, depth) pair: the arithmetic of ego_point / select_pillar, two at a time
-template <bool POW2>
-__device__ __forceinline__ void pillars_of_two_rows(const CameraTransform& T, const ColumnTerms& ct, float v0, float v1, float depth,
-                                                    float offx, float offy, float offz, float kx, float ky, float Xf, float Yf,
-                                                    float z_lo, float z_hi, int Y, int& cur0, int& cur1) {
-    const unsigned long long vd = f2_mul(f2_pack(v0, v1), f2_pack(depth, depth));           // v*d, fiery.py:202
-    float vd0, vd1;
-    f2_unpack(vd, vd0, vd1);
-    unsigned long long p[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const unsigned long long prod = f2_pack(__fmul_rn(T.m[r * 3 + 1], vd0), __fmul_rn(T.m[r * 3 + 1], vd1));
-        unsigned long long acc = f2_add(f2_pack(ct.a[r], ct.a[r]), prod);                    // (M[r][0]*(u*d) + M[r][1]*(v*d))
-        acc = f2_add(acc, f2_pack(ct.c[r], ct.c[r]));                                        //  + M[r][2]*d
-        p[r] = f2_add(acc, f2_pack(T.t[r], T.t[r]));                                         //  + t_r          fiery.py:204-205
-    }
-    // p - off == p + (-off) exactly
-    const unsigned long long ax = f2_add(p[0], f2_pack(-offx, -offx)), ay = f2_add(p[1], f2_pack(-offy, -offy));
-    const unsigned long long az = f2_add(p[2], f2_pack(-offz, -offz));
-    float sx0, sx1, sy0, sy1, az0, az1;
-    if (POW2) {
-        f2_unpack(f2_mul(ax, f2_pack(kx, kx)), sx0, sx1);                                    // exact scale, fiery.py:236
-        f2_unpack(f2_mul(ay, f2_pack(ky, ky)), sy0, sy1);
-    } else {
-        float a0, a1;
-        f2_unpack(ax, a0, a1); sx0 = __fdiv_rn(a0, kx); sx1 = __fdiv_rn(a1, kx);
-        f2_unpack(ay, a0, a1); sy0 = __fdiv_rn(a0, ky); sy1 = __fdiv_rn(a1, ky);
-    }
-    f2_unpack(az, az0, az1);
-    cur0 = select_pillar(sx0, sy0, az0, Xf, Yf, z_lo, z_hi, static_cast<int>(sx0) * Y + static_cast<int>(sy0));
-    cur1 = select_pillar(sx1, sy1, az1, Xf, Yf, z_lo, z_hi, static_cast<int>(sx1) * Y + static_cast<int>(sy1));
-}
-
-// Geometry of the tile: the pillar (rank, fiery.py:236-256; -1 = masked) of every point, evaluated with the reference
-// arithmetic, reduced on the fly to what the pooling loop consumes:
+// The geometry of the tile comes from the plan (lift_plan.cu: get_geometry + voxel index / mask / rank of every point,
+// fiery.py:193-208,236-256, reduced to pillar runs per (depth, column) pair).  Here the runs of the tile are expanded into what the
+// pooling loop consumes:
 //   ev[unit][row]      bit j (slot j = dd*4 + col: depth DD*unit + dd, column col) set <=> pair j changes pillar between
 //                      row-1 and row; bit 4*DD + j: ... and the run that ends sits on a valid pillar (it must be flushed, the
 //                      others are only cleared)
 //   pillar[row][pair]  written only where it is read: the last row of every run
-//   touched[pillar]    the layout pass's map of pillars that receive something, marked at every run start
-// thread = (pair, row range); the NRS ranges of a pair sit in adjacent lanes and hand their last pillar to the next range.
-template <bool POW2, int NT, int DD, bool PACKED = false>
-__device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem, int w0,
-                                                    unsigned char* touched) {
-    constexpr int NRS = NT / COLS_NPAIR >= 4 ? 4 : (NT / COLS_NPAIR >= 2 ? 2 : 1);
+// thread = (depth, column) pair; a pair has ~2.8 runs on average, so this is a few dozen instructions per thread (the 37
+// instructions per POINT of the reference arithmetic are spent once per batch in the plan kernel, not per tile pass).
+template <int NT, int DD>
+__device__ __forceinline__ void expand_plan(const ColsLayout& L, unsigned char* smem, const unsigned char* __restrict__ rec) {
     static_assert(NT >= COLS_NPAIR, "one thread per (depth, column) pair at least");
-    const float* s_cam = reinterpret_cast<const float*>(smem + L.off_cam);
-    const float* s_u = reinterpret_cast<const float*>(smem + L.off_u);
-    const float* s_v = reinterpret_cast<const float*>(smem + L.off_v);
-    const float* s_d = reinterpret_cast<const float*>(smem + L.off_d);
-    int* s_pillar = reinterpret_cast<int*>(smem + L.off_pillar);
-    unsigned* s_ev = reinterpret_cast<unsigned*>(smem + L.off_ev);
-    CameraTransform T;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) T.m[i] = s_cam[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) T.t[i] = s_cam[9 + i];
-    const float offx = P.grid.off[0], offy = P.grid.off[1], offz = P.grid.off[2];
-    const float kx = POW2 ? P.grid.inv_res[0] : P.grid.res[0], ky = POW2 ? P.grid.inv_res[1] : P.grid.res[1];
-    const float Xf = static_cast<float>(P.grid.X), Yf = static_cast<float>(P.grid.Y);
-    const float z_lo = P.grid.z_lo, z_hi = P.grid.z_hi;
-    const int Y = P.grid.Y;
-    const int hh = L.hh;
-    const int pair = threadIdx.x / NRS, rs = threadIdx.x % NRS;
-    const bool idle = pair >= COLS_NPAIR;                    // NT is not always a multiple of the pair count
-    const int d = idle ? 0 : pair >> 2, col = pair & 3;
-    const int unit = d / DD, j = (d % DD) * 4 + col;
-    const bool split = hh >= 2 * NRS;                       // short columns: one lane of the pair walks all rows
-    const int h_lo = idle ? 0 : (split ? (hh * rs) / NRS : 0);
-    const int h_hi = idle ? 0 : (split ? (hh * (rs + 1)) / NRS : (rs == 0 ? hh : 0));
-    const bool dead = d >= P.D || w0 + col >= P.ww;
-
-    unsigned* ev = s_ev + unit * COLS_EVS;
-    int* tab = s_pillar + (idle ? 0 : pair);
-    auto run_ends = [&](int h, int before, int now) {        // rows h-1 | h lie in different pillars
-        atomicOr(ev + h, (1u << j) | (before >= 0 ? (1u << (4 * DD + j)) : 0u));
-        if (before >= 0) tab[(h - 1) * COLS_NPAIR] = before;
-        if (touched && now >= 0) touched[now] = 0x0f;       // one bit per channel quarter of the layout pass
-    };
-
-    int first = -1, prev = -1;
-    if (!dead && h_lo < h_hi) {
-        const float depth = s_d[d];
-        const ColumnTerms ct = column_terms(T, s_u[col], depth);
-        int h = h_lo;
-        if (PACKED) {                                                         // two rows per trip, packed adds
-            for (; h + 1 < h_hi; h += 2) {
-                int cur0, cur1;
-                pillars_of_two_rows<POW2>(T, ct, s_v[h], s_v[h + 1], depth, offx, offy, offz, kx, ky, Xf, Yf, z_lo, z_hi, Y, cur0, cur1);
-                if (h == h_lo) first = cur0;
-                else if (cur0 != prev) run_ends(h, prev, cur0);
-                if (cur1 != cur0) run_ends(h + 1, cur0, cur1);
-                prev = cur1;
-            }
-        }
-#pragma unroll 2
-        for (; h < h_hi; ++h) {
-            float p[3];
-            ego_point(T, ct, s_v[h], depth, p);                               // fiery.py:199-205
-            const float ax = __fsub_rn(p[0], offx), ay = __fsub_rn(p[1], offy), az = __fsub_rn(p[2], offz);
-            const float sx = POW2 ? __fmul_rn(ax, kx) : __fdiv_rn(ax, kx);    // fiery.py:236 (x scale exact when res is 2^k)
-            const float sy = POW2 ? __fmul_rn(ay, ky) : __fdiv_rn(ay, ky);
-            const int rank = static_cast<int>(sx) * Y + static_cast<int>(sy); // truncation, fiery.py:237,252-256
-            const int cur = select_pillar(sx, sy, az, Xf, Yf, z_lo, z_hi, rank);   // mask, fiery.py:240-247
-            if (h == h_lo) first = cur;
-            else if (cur != prev) run_ends(h, prev, cur);
-            prev = cur;
-        }
+    const int pair = threadIdx.x;
+    if (pair >= COLS_NPAIR) return;
+    int* tab = reinterpret_cast<int*>(smem + L.off_pillar) + pair;
+    unsigned m = __ldg(reinterpret_cast<const unsigned*>(rec + PLAN_OFF_MASK) + pair);
+    const int* runs = reinterpret_cast<const int*>(rec + PLAN_OFF_RUNS) + __ldg(reinterpret_cast<const unsigned short*>(rec + PLAN_OFF_OFF) + pair);
+    const int d = pair >> 2, col = pair & 3;
+    const int j = (d % DD) * 4 + col;
+    unsigned* ev = reinterpret_cast<unsigned*>(smem + L.off_ev) + (d / DD) * COLS_EVS;
+    int cur = __ldg(runs);
+    while (m) {
+        const int h = __ffs(m) - 1;                       // rows h-1 | h lie in different pillars
+        m &= m - 1;
+        const int nxt = __ldg(++runs);
+        atomicOr(ev + h, (1u << j) | (cur >= 0 ? (1u << (4 * DD + j)) : 0u));
+        if (cur >= 0) tab[(h - 1) * COLS_NPAIR] = cur;
+        cur = nxt;
     }
-    const int before = __shfl_up_sync(0xffffffffu, prev, 1);   // last pillar of the previous row range of this pair
-    if (h_lo < h_hi) {
-        if (rs > 0 && split) {
-            if (first != before) run_ends(h_lo, before, first);
-        } else if (touched && first >= 0) {
-            touched[first] = 0x0f;                                  // row 0 starts a run
-        }
-        if (h_hi == hh) tab[(hh - 1) * COLS_NPAIR] = prev;          // the run that reaches the last row
-    }
+    tab[(L.hh - 1) * COLS_NPAIR] = cur;                   // the run that reaches the last row
 }
 
 // ---- half-precision head tensors (AMP: Encoder.depth_layer emits fp16, encoder.py:96 under PRECISION 16) ------------------------
@@ -385,7 +270,7 @@ __device__ __forceinline__ void flush_depth(unsigned long long (&acc)[CPL][DD][2
 
 // CPL channels per lane, DD depths per unit: a unit is 64 / CPL lanes, a tile 48 / DD units.
 //   CPL 2, DD 2: 768 threads (a unit is a warp)      CPL 2, DD 4: 384 threads      CPL 4, DD 4: 192 threads (a unit is a half-warp)
-template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false, bool PACKED = false>
+template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false>
 __global__ void __launch_bounds__((COLS_DPAD / DD) * (64 / CPL), MINB)
 lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const LiftParams P) {
     constexpr int LPU = 64 / CPL;                     // lanes per unit
@@ -402,6 +287,7 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
     const int w0 = wtile * WT;
     const int tid = threadIdx.x;
     const int hh = L.hh;
+    // (img_local indexes the plan's tile records and the accumulator; img the head tensor)
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     if (HALF) {
@@ -416,32 +302,13 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
         if (P.use_depth) tma_load_4d(smem + L.off_prob, &head_maps.depth, bar, w0, 0, 0, img);
         tma_load_5d(smem + L.off_ctx, &head_maps.ctx, bar, w0, 0, 0, 0, img);
     }
-    {   // constants of the tile
-        float* s_u = reinterpret_cast<float*>(smem + L.off_u);
-        float* s_v = reinterpret_cast<float*>(smem + L.off_v);
-        float* s_d = reinterpret_cast<float*>(smem + L.off_d);
-        if (tid < WT) s_u[tid] = (w0 + tid < P.ww) ? P.fu[w0 + tid] : 0.f;
-        if (tid >= 32 && tid < 64) s_v[tid - 32] = P.fv[min(tid - 32, hh - 1)];
-        if (tid >= 64 && tid < 64 + COLS_DPAD) s_d[tid - 64] = (tid - 64 < P.D) ? P.fd[tid - 64] : 0.f;
+    {
         unsigned* s_ev = reinterpret_cast<unsigned*>(smem + L.off_ev);
         for (int i = tid; i < NU * COLS_EVS; i += NT) s_ev[i] = 0u;
     }
-    // one lane composes R @ K^-1 (fiery.py:203); the head tile stays in flight through the whole geometry phase
-    if (tid == NT - 1) {
-        CameraTransform T;
-        load_camera(P.calib_mode, P.calib_a, P.calib_b, img, T);
-        float* s_cam = reinterpret_cast<float*>(smem + L.off_cam);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) s_cam[i] = T.m[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) s_cam[9 + i] = T.t[i];
-    }
-    __syncthreads();                                  // constants, camera and the mbarrier are set up
-    {
-        unsigned char* touched = P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
-        if (P.grid.pow2[0] && P.grid.pow2[1]) stage_geometry_cols<true, NT, DD, PACKED>(P, L, smem, w0, touched);
-        else stage_geometry_cols<false, NT, DD, PACKED>(P, L, smem, w0, touched);
-    }
+    __syncthreads();                                  // event words cleared, the mbarrier is set up
+    // geometry of the tile: the runs the plan kernel computed for it (the head tile stays in flight meanwhile)
+    expand_plan<NT, DD>(L, smem, P.plan_tiles + static_cast<size_t>(blockIdx.x) * PLAN_TILE_BYTES);
     if (HALF) widen_half_tile<NT>(P, L, smem);         // fp16 pieces -> the fp32 tile, in place
     else mbar_wait(bar, 0);                           // head tile has landed
     softmax_cols<NT>(P, L, smem);
@@ -504,7 +371,7 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
 
 int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams& P, int channels_per_lane);
 
-template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false, bool PACKED = false>
+template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false>
 static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStream_t stream) {
     constexpr int NU = COLS_DPAD / DD, NT = NU * (64 / CPL);
     const ColsLayout L(P.hh, P.C, NU);
@@ -513,9 +380,9 @@ static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStre
     FIERY_CUDA_CHECK(cudaGetDevice(&dev_id));
     bool& configured = configured_on[dev_id & 63];
     if (!configured) {
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // ask for the full shared-memory carve-out (3 x 74 KB per SM for the reference shape)
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PACKED>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
@@ -530,7 +397,7 @@ static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStre
         if (rc != FIERY_OK) return rc;
     }
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
-    lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PACKED><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
+    lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }
@@ -561,8 +428,6 @@ int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stre
         case 6: return launch_forward_cols_t<4, 3, 3>(P, head, stream);
         case 7: return launch_forward_cols_t<2, 4, 3>(P, head, stream);
         case 8: return launch_forward_cols_t<2, 2, 2, 2>(P, head, stream);
-        case 12: return launch_forward_cols_t<2, 2, 2, 1, false, true>(P, head, stream);     // packed geometry
-        case 13: return launch_forward_cols_t<2, 3, 2, 2, false, true>(P, head, stream);
         default: break;
     }
 #endif

@@ -24,6 +24,8 @@ from . import _lib
 from .geometry import (_require_cuda, _stream_ptr, bev_offset_fp32, calculate_birds_eye_view_parameters, create_frustum,
                        split_frustum, z_valid_interval)
 
+_PLAN_OFF_COUNTS = 192 * 4 + 192 * 2 + 64 * 2      # mask[192] u32, off[192] u16, soff[64] u16, then (n_runs, n_stream) u32
+
 _TORCH_TO_DTYPE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16}
 
 # Half-precision head tensors (AMP, baseline.yml PRECISION 16): False (default) = the tensor is widened to fp32 on the device
@@ -192,10 +194,30 @@ class LiftSplat(nn.Module):
         return _lib.CALIB_RAW, intrinsics.float().contiguous(), extrinsics.float().contiguous()
 
     # -- public entry points --------------------------------------------------------------------------------------
-    def forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:
+    def forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
+                plan: Optional[torch.Tensor] = None) -> torch.Tensor:
         """head (B'*n, D+C, h, w) [= Encoder.depth_layer output, encoder.py:96], intrinsics (B', n, 3, 3),
-        extrinsics (B', n, 4, 4) -> BEV features (B', C, X, Y) float32 (fiery.py:225-227 allocates float32)."""
-        return _LiftSplatFunction.apply(head, intrinsics, extrinsics, self)
+        extrinsics (B', n, 4, 4) -> BEV features (B', C, X, Y) float32 (fiery.py:225-227 allocates float32).
+        ``plan``: the geometry of this calibration from ``self.plan(intrinsics, extrinsics)`` -- pass it while the camera rig
+        is static and the per-call geometry pass disappears; ``None`` computes it inside the call."""
+        return _LiftSplatFunction.apply(head, intrinsics, extrinsics, self, plan)
+
+    def plan(self, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:
+        """The geometry plan of a batch of calibrations (fiery_lift_plan): where every frustum point lands -- get_geometry
+        (fiery.py:193-208) + voxel index / mask / rank (fiery.py:236-256) -- as pillar runs, in a device byte tensor.  Valid for
+        forward and backward calls with the same (B', n) and these calibrations."""
+        _require_cuda(intrinsics, "intrinsics")
+        lib = _lib.load()
+        dev = intrinsics.device
+        c = self._constants(dev)
+        B, n = intrinsics.shape[:2]
+        mode, a, b = self._calibration(intrinsics, extrinsics.to(dev))
+        desc = self._desc(c, B, n, torch.float32, mode, _lib.BEV_NCHW)
+        buf = torch.empty(max(1, int(lib.fiery_lift_plan_bytes(desc))), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.fiery_lift_plan(desc, a.data_ptr(), b.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(), c["d"].data_ptr(),
+                                           buf.data_ptr(), _stream_ptr(dev)), "fiery_lift_plan")
+        return buf
 
     def point_indices(self, intrinsics: torch.Tensor, extrinsics: torch.Tensor):
         """Integer voxel coordinates of every frustum point, as the reference computes them at fiery.py:236-256.
@@ -233,12 +255,29 @@ class LiftSplat(nn.Module):
                                                      _stream_ptr(dev)), "fiery_compose_calibration")
         return comb, trans
 
+    def plan_summary(self, plan: torch.Tensor, n_frames: int, n_cameras: int) -> Dict[str, int]:
+        """Counts read back from a plan buffer (layout: fiery_b200/csrc/lift_plan.cuh): pillar runs, backward stream entries and
+        pillars that receive a point.  Diagnostic (bench.py uses it for the per-kernel algorithmic bytes); synchronises."""
+        c = self._constants(plan.device)
+        n_tiles = n_frames * n_cameras * ((c["w"] + 3) // 4)
+        X, Y, _ = c["dim"]
+        touched_bytes = (n_frames * X * Y + 127) // 128 * 128
+        tile_bytes = (plan.numel() - touched_bytes) // max(1, n_tiles)
+        counts = plan[:n_tiles * tile_bytes].view(n_tiles, tile_bytes)[:, _PLAN_OFF_COUNTS:_PLAN_OFF_COUNTS + 8].contiguous().view(torch.int32)
+        touched = plan[n_tiles * tile_bytes:n_tiles * tile_bytes + n_frames * X * Y]
+        return {"runs": int(counts[:, 0].sum()), "stream_entries": int(counts[:, 1].sum()), "touched_pillars": int(touched.ne(0).sum()),
+                "tile_record_bytes": int(tile_bytes)}
+
     # -- CUDA graph and host-buffer entry points ------------------------------------------------------------------------
-    def capture(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> "GraphedLift":
+    def capture(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
+                static_calibration: bool = False) -> "GraphedLift":
         """Captures one forward lift of these (device-resident, static) tensors into a CUDA graph.  ``g = lift.capture(...)``;
-        ``bev = g()`` replays it: one graph launch instead of descriptor encoding + two kernel launches from Python.
-        The returned BEV tensor is the graph's static output buffer (overwritten by the next replay).  Inference only."""
-        return GraphedLift(self, head, intrinsics, extrinsics)
+        ``bev = g()`` replays it: one graph launch instead of descriptor encoding + kernel launches from Python.
+        ``static_calibration=True``: the calibration tensors never change between replays (a fixed camera rig), so the geometry
+        plan is computed once here and the replay only runs the tile kernels and layout passes; otherwise the plan kernels are
+        part of every replay.  The returned BEV tensor is the graph's static output buffer (overwritten by the next replay).
+        Inference only."""
+        return GraphedLift(self, head, intrinsics, extrinsics, static_calibration)
 
     def lift_from_host(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
                        out: Optional[torch.Tensor] = None, device: Optional[torch.device] = None,
@@ -296,7 +335,7 @@ class LiftSplat(nn.Module):
 
     # -- raw launches (used by the autograd function and by bench.py) ------------------------------------------------
     def _launch_forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
-                        scratch: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        scratch: Optional[torch.Tensor] = None, plan: Optional[torch.Tensor] = None) -> torch.Tensor:
         _require_cuda(head, "head")
         lib = _lib.load()
         dev = head.device
@@ -318,25 +357,27 @@ class LiftSplat(nn.Module):
             if self.output_layout == "channels_last":
                 desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NHWC)
                 store = torch.zeros((B, X, Y, C), dtype=torch.float32, device=dev)
-                out, scratch_ptr = store.permute(0, 3, 1, 2), 0
+                out = store.permute(0, 3, 1, 2)
             else:
                 desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NCHW)
                 store = torch.empty((B, C, X, Y), dtype=torch.float32, device=dev)
                 out = store
-                if scratch is None and B:
-                    pooled = int(lib.fiery_lift_scratch_bytes(desc))
-                    scratch = _scratch.get(dev, pooled)
-                scratch_ptr = scratch.data_ptr() if B else 0
+            if plan is not None and plan.numel() < int(lib.fiery_lift_plan_bytes(desc)):
+                raise ValueError("plan was made for another batch shape: rebuild it with LiftSplat.plan(intrinsics, extrinsics)")
+            if scratch is None and B:
+                pooled = int(lib.fiery_lift_scratch_bytes(desc))
+                scratch = _scratch.get(dev, pooled)            # zero-filled once; the kernels keep its accumulator part zeroed
+            scratch_ptr = scratch.data_ptr() if B else 0
             status = lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
                                             c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
-                                            _stream_ptr(dev))
+                                            plan.data_ptr() if plan is not None else 0, _stream_ptr(dev))
             if status != 0 and pooled:
                 _scratch.discard(dev, pooled)          # a launch sequence that stopped half way may have left it dirty
             _lib.check(status, "fiery_lift_forward")
         return out
 
     def _launch_backward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
-                         grad_bev: torch.Tensor) -> torch.Tensor:
+                         grad_bev: torch.Tensor, plan: Optional[torch.Tensor] = None) -> torch.Tensor:
         lib = _lib.load()
         dev = head.device
         c = self._constants(dev)
@@ -352,11 +393,13 @@ class LiftSplat(nn.Module):
         desc = self._desc(c, B, n, head.dtype, mode, layout)
         grad_head = torch.empty_like(head)
         with torch.cuda.device(dev):
-            ws_bytes = int(lib.fiery_lift_workspace_bytes(desc))
-            ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=dev) if ws_bytes else None
+            ws = None
+            if plan is None or layout == _lib.BEV_NCHW:        # re-layout of an NCHW gradient and/or room for the plan records
+                ws = torch.empty(max(1, int(lib.fiery_lift_workspace_bytes(desc)) // 4), dtype=torch.float32, device=dev)
             _lib.check(lib.fiery_lift_backward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
                                                c["v"].data_ptr(), c["d"].data_ptr(), g.data_ptr(), grad_head.data_ptr(),
-                                               ws.data_ptr() if ws is not None else 0, _stream_ptr(dev)),
+                                               ws.data_ptr() if ws is not None else 0,
+                                               plan.data_ptr() if plan is not None else 0, _stream_ptr(dev)),
                        "fiery_lift_backward")
         return grad_head
 
@@ -364,27 +407,30 @@ class LiftSplat(nn.Module):
 class GraphedLift:
     """A captured forward lift (see ``LiftSplat.capture``)."""
 
-    def __init__(self, module: LiftSplat, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor):
+    def __init__(self, module: LiftSplat, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
+                 static_calibration: bool = False):
         _require_cuda(head, "head")
         self.module, self.inputs = module, (head, intrinsics, extrinsics)
         dev = head.device
+        self.plan = module.plan(intrinsics, extrinsics) if static_calibration and intrinsics.shape[0] else None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(2):                       # warm-up outside capture: attribute setup, scratch allocation
-                module._launch_forward(head, intrinsics, extrinsics)
+                module._launch_forward(head, intrinsics, extrinsics, plan=self.plan)
         torch.cuda.current_stream(dev).wait_stream(side)
         # the graph owns its accumulation scratch (zeroed once here; every replay leaves it zeroed again)
         c = module._constants(dev)
         B, n = intrinsics.shape[:2]
         self.scratch = None
-        if module.output_layout != "channels_last" and B:
-            desc = module._desc(c, B, n, head.dtype, _lib.CALIB_RAW, _lib.BEV_NCHW)
-            self.scratch = torch.zeros(int(_lib.load().fiery_lift_scratch_bytes(desc)) // 4, dtype=torch.float32, device=dev)
+        if B:
+            layout = _lib.BEV_NHWC if module.output_layout == "channels_last" else _lib.BEV_NCHW
+            desc = module._desc(c, B, n, head.dtype, _lib.CALIB_RAW, layout)
+            self.scratch = torch.zeros(max(1, int(_lib.load().fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():
-            self.output = module._launch_forward(head, intrinsics, extrinsics, scratch=self.scratch)
+            self.output = module._launch_forward(head, intrinsics, extrinsics, scratch=self.scratch, plan=self.plan)
 
     def __call__(self) -> torch.Tensor:
         self.graph.replay()
@@ -396,7 +442,7 @@ class _LiftSplatFunction(torch.autograd.Function):
     in backward is cheaper than saving the 124 MB/frame frustum volume the reference keeps alive)."""
 
     @staticmethod
-    def forward(ctx, head, intrinsics, extrinsics, module: LiftSplat):
+    def forward(ctx, head, intrinsics, extrinsics, module: LiftSplat, plan=None):
         # Under AMP (baseline.yml PRECISION 16) depth_layer emits fp16; the reference's softmax autocasts to fp32 and the
         # fp32 x fp16 outer product promotes to fp32 (encoder.py:99-100), so the lift itself is fp32 there too.  The forward
         # tile kernel can read the fp16 tensor itself (NATIVE_FP16_FORWARD); otherwise, and for bf16, the logits are widened
@@ -404,8 +450,11 @@ class _LiftSplatFunction(torch.autograd.Function):
         ctx.head_dtype = head.dtype
         native = head.dtype == torch.float32 or (head.dtype == torch.float16 and NATIVE_FP16_FORWARD)
         head_in = head if native else head.float()
-        out = module._launch_forward(head_in, intrinsics, extrinsics)
+        if plan is None and ctx.needs_input_grad[0] and intrinsics.shape[0]:
+            plan = module.plan(intrinsics.to(head.device), extrinsics)     # the geometry is computed once and shared with the backward
+        out = module._launch_forward(head_in, intrinsics, extrinsics, plan=plan)
         ctx.module = module
+        ctx.plan = plan
         ctx.save_for_backward(head_in, intrinsics, extrinsics)
         return out
 
@@ -414,8 +463,8 @@ class _LiftSplatFunction(torch.autograd.Function):
         head, intrinsics, extrinsics = ctx.saved_tensors
         if head.dtype != torch.float32:
             head = head.float()                      # the backward kernel reads an fp32 head tensor
-        grad_head = ctx.module._launch_backward(head, intrinsics, extrinsics, grad_bev)
-        return grad_head.to(ctx.head_dtype), None, None, None     # calibration is data: no gradient (geometry.py:300)
+        grad_head = ctx.module._launch_backward(head, intrinsics, extrinsics, grad_bev, plan=ctx.plan)
+        return grad_head.to(ctx.head_dtype), None, None, None, None     # calibration is data: no gradient (geometry.py:300)
 
 
 def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):

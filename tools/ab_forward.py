@@ -41,14 +41,15 @@ def runner(layout, out, scratch):
     desc = lift._desc(c, F, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, layout)
     def run():
         _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
-                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr() if scratch is not None else 0, stream), "fwd")
+                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), None, stream), "fwd")
     return run, desc
 
 
 res = {"workload": wl, "tile": {}, "layout_pass": {}}
 ref = None
 acc = torch.zeros((F, X, Y, cfg.out_channels), dtype=torch.float32, device=dev)
-run_nhwc, _ = runner(_lib.BEV_NHWC, acc, None)
+_d_nhwc = lift._desc(c, F, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, _lib.BEV_NHWC)
+run_nhwc, _ = runner(_lib.BEV_NHWC, acc, torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(_d_nhwc)) // 4), dtype=torch.float32, device=dev))
 for v in variants:
     os.environ["FIERY_COLS_VARIANT"] = str(v)
     try:
@@ -85,7 +86,7 @@ for combo in combos:
     out_nchw.fill_(float("nan"))
     run(); torch.cuda.synchronize()
     err = float((out_nchw - ref_nchw).norm() / ref_nchw.norm())
-    clean = bool((scratch == 0).all().item())
+    clean = bool((scratch[:int(lib.fiery_lift_scratch_zeroed_bytes(desc)) // 4] == 0).all().item())
     for _ in range(3):
         run()
     mean, mn = timed(run)
@@ -96,7 +97,7 @@ for combo in combos:
         sp = s.cuda_stream
         def run_s():
             _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
-                                              c["d"].data_ptr(), out_nchw.data_ptr(), scratch.data_ptr(), sp), "fwd")
+                                              c["d"].data_ptr(), out_nchw.data_ptr(), scratch.data_ptr(), None, sp), "fwd")
         run_s(); torch.cuda.synchronize()
         with torch.cuda.graph(g, stream=s):
             run_s()
@@ -105,7 +106,7 @@ for combo in combos:
     gmean, gmn = timed(g.replay)
     torch.cuda.synchronize()
     err2 = float((out_nchw - ref_nchw).norm() / ref_nchw.norm())
-    clean2 = bool((scratch == 0).all().item())
+    clean2 = bool((scratch[:int(lib.fiery_lift_scratch_zeroed_bytes(desc)) // 4] == 0).all().item())
     # backward (eager, through the host layer: workspace allocation + re-layout + tile kernel)
     gh = lift._launch_backward(head, K_d, E_d, gout)
     if combo == combos[0]:
@@ -115,7 +116,7 @@ for combo in combos:
         lift._launch_backward(head, K_d, E_d, gout)
     bmean, bmn = timed(lambda: lift._launch_backward(head, K_d, E_d, gout))
     res["layout_pass"][combo] = {"us_mean": mean, "graph_us_mean": gmean, "graph_us_min": gmn, "rel_err": max(err, err2),
-                                 "scratch_clean": clean and clean2, "launches": int(lib.fiery_lift_forward_launches(desc)),
+                                 "scratch_clean": clean and clean2, "launches": int(lib.fiery_lift_forward_launches(desc, 0)),
                                  "bwd_us_mean": bmean, "bwd_rel_err_vs_first": berr}
     print("chains:min_tiles", combo, res["layout_pass"][combo], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

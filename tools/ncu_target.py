@@ -34,5 +34,5 @@ else:
     scratch = torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
     for _ in range(4):
         _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
-                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), _stream_ptr(dev)), "fwd")
+                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), None, _stream_ptr(dev)), "fwd")
 torch.cuda.synchronize()
