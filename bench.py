@@ -7,7 +7,7 @@ One "step" = one pass of the hot path {head tensor, intrinsics, extrinsics} -> B
 synthetic frames.  Prints ONE JSON line (rank 0).
 
   value      whole-job frames/s, inputs resident in HBM, through the public Python API (LiftSplat.capture -> C ABI): one step =
-             geometry plan + tile kernels + layout passes of the whole batch (nothing is cached between steps)
+             tile kernels (geometry evaluated inside) + layout passes of the whole batch (nothing is cached between steps)
   e2e        same metric with HOST (pinned) inputs and a host copy of the BEV inside the timed region
   roofline   the PATH against the measured HBM copy bandwidth (MEASURED_PEAKS.json): algorithmic bytes of the step / step time;
              `kernels` lists every kernel of the step with its OWN algorithmic bytes, the duration of the launches the step really
@@ -261,9 +261,9 @@ def main():
         return times
 
     # ---- value: device-resident inputs through the public API ----------------------------------------------------------
-    # LiftSplat.capture() records the forward lift (TMA descriptors + the plan-kernel / tile-kernel / layout-pass chains of every
-    # frame group, forked over internal streams) into a CUDA graph once; a step is one replay and recomputes EVERYTHING of the path,
-    # the geometry plan included.  value_static_rig: the same with the plan cached (LiftSplat.capture(static_calibration=True), the
+    # LiftSplat.capture() records the forward lift (TMA descriptors + the tile-kernel / layout-pass chains of every frame group, forked
+    # over internal streams) into a CUDA graph once; a step is one replay and recomputes EVERYTHING of the path, the geometry included
+    # (the tile kernels evaluate it).  value_static_rig: the same with the geometry plan cached (capture(static_calibration=True), the
     # inference case of a fixed camera rig) -- reported next to the value, never as the value.
     def step_eager():
         with torch.no_grad():
@@ -333,11 +333,11 @@ def main():
     stream = _stream_ptr(dev)
     layout_code = _lib.BEV_NHWC if args.layout == "channels_last" else _lib.BEV_NCHW
     desc = lift._desc(c, frames, cfg.n_cameras, head_dtype, _lib.CALIB_RAW, layout_code)
-    launches_per_step = int(lib.fiery_lift_forward_launches(desc, 0))
+    launches_per_step = int(lib.fiery_lift_forward_launches(desc))
     scratch = torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
     out_buf = (torch.zeros((frames, X, Y, cfg.out_channels), dtype=torch.float32, device=dev) if layout_code == _lib.BEV_NHWC
                else torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32, device=dev))
-    KIND = {0: "lift_plan_kernel", 1: "lift_forward_cols_kernel", 2: "finalize_tma_kernel"}
+    KIND = {1: "lift_forward_cols_kernel", 2: "finalize_tma_kernel"}
     per_kind = {k: [] for k in KIND}
     cap = 64
     ms_arr, kind_arr, n_arr = (ctypes.c_float * cap)(), (ctypes.c_int32 * cap)(), ctypes.c_int32(0)
@@ -440,9 +440,7 @@ def main():
         ps = lift.plan_summary(plan_d, frames, cfg.n_cameras)
         touched_rows = ps["touched_pillars"]
         row_bytes = cfg.out_channels * 4
-        plan_out = 4 * (ps["runs"] + ps["stream_entries"])
-        own = {"lift_plan_kernel": plan_out + touched_rows,                                # run lists + stream lists + marks (not HBM-bound)
-               "lift_forward_cols_kernel": head_bytes + touched_rows * row_bytes,             # read head once, each touched row written once
+        own = {"lift_forward_cols_kernel": head_bytes + touched_rows * row_bytes,             # read head once, each touched row written once
                "finalize_tma_kernel": 2 * touched_rows * row_bytes + bev_bytes}               # gather + re-zero touched rows, write the BEV
         traffic = load_traffic(cfg.name) if args.head_dtype == "f32" else {}
         kernels = []
@@ -469,7 +467,7 @@ def main():
             "config": {**config_dict(cfg, args, world),
                        "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                        "l2": "flushed before every timed step (256 MiB write); step time = CUDA events around the step",
-                       "api": "value: LiftSplat.capture() CUDA-graph replay (plan + tile kernels + layout passes every step); "
+                       "api": "value: LiftSplat.capture() CUDA-graph replay (tile kernels incl. geometry + layout passes every step); "
                               "value_static_rig: capture(static_calibration=True); value_eager: LiftSplat.forward; "
                               "e2e: LiftSplat.lift_from_host (pinned host in/out, 3-stream chunk pipeline)",
                        "host": {"numa_node": numa[0], "cores_bound": numa[1], "note": numa[2]},
@@ -477,7 +475,7 @@ def main():
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(head_h.numel() * head_h.element_size() + K_h.numel() * 4 + E_h.numel() * 4),
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},
-            # kernels of the timed `value` region: per step and frame group one plan kernel, one tile kernel (+ one layout pass)
+            # kernels of the timed `value` region: per step and frame group one tile kernel (+ one layout pass)
             "gpu_launches": launches_per_step * S,
             "roofline": {"bound": "hbm", "kernel": "path: " + " + ".join(k["kernel"] for k in kernels),
                          "achieved": gbs(alg_bytes, ms_dev), "peak": peak, "peak_source": peak_src, "unit": "GB/s",

@@ -57,15 +57,26 @@ def is_current() -> bool:
         return fh.read().strip() == _source_hash()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compiles every .cu under csrc/ for sm_100a into fiery_b200/libfiery_b200.so; returns its path."""
+def build(force: bool = False, verbose: bool = False, out: str = None, obj_suffix: str = "") -> str:
+    """Compiles every .cu under csrc/ for sm_100a into fiery_b200/libfiery_b200.so; returns its path.
+    ``out`` / ``obj_suffix``: build a second library next to it (experiment builds with FIERY_NVCC_EXTRA) without touching the
+    in-tree one."""
+    if out is not None:
+        return _build_to(out, obj_suffix or ".ab", verbose)
     if not force and is_current():
         return LIB_PATH
+    _build_to(LIB_PATH, "", verbose)
+    with open(STAMP_PATH, "w") as fh:
+        fh.write(_source_hash())
+    return LIB_PATH
+
+
+def _build_to(lib_path: str, obj_suffix: str, verbose: bool) -> str:
     nvcc = _nvcc()
     objs = []
     procs = []
     for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, src.replace(".cu", obj_suffix + ".o"))
         cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "--use_fast_math=false"], *_extra_flags(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -82,16 +93,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(f"nvcc failed on {src}", file=sys.stderr)
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path, *objs, "-lcudart_static", "-ldl", "-lrt", "-lpthread"]
     subprocess.run(link, check=True)
-    with open(STAMP_PATH, "w") as fh:
-        fh.write(_source_hash())
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--out", default=None, help="write an experiment build here instead of the in-tree library")
     a = ap.parse_args()
-    print(build(force=a.force, verbose=a.verbose))
+    print(build(force=a.force, verbose=a.verbose, out=a.out))

@@ -137,12 +137,12 @@ int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels
 // launchers defined next to their kernels
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, void* scratch, const void* plan,
                         cudaStream_t);
-int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, cudaStream_t stream);
+int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, int want_streams, cudaStream_t stream);
 int lift_chunk_frames(const LiftParams& P);
-size_t lift_scratch_frame_bytes(const LiftParams& P, size_t* accum_bytes_out);
+size_t lift_scratch_bytes(const LiftParams& P);
 void lift_set_max_chunk_frames(int n);
 void lift_set_timer(LaunchTimer* t);
-int lift_forward_launches(const LiftParams& P, int has_plan);
+int lift_forward_launches(const LiftParams& P);
 size_t lift_backward_relayout_bytes(const LiftParams& P);
 int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, float* workspace, const void* plan, cudaStream_t);
 int launch_point_indices(const LiftParams& P, int64_t* idx_out, uint8_t* valid_out, int32_t* pillar_out, cudaStream_t);
@@ -178,7 +178,7 @@ static int make_params(const fiery_lift_desc_t* d, const float* calib_a, const f
     P.head_channels = d->channels + (P.use_depth ? d->depth_bins : 0);
     P.calib_mode = d->calib_mode;
     P.calib_a = calib_a; P.calib_b = calib_b; P.fu = fu; P.fv = fv; P.fd = fd;
-    P.accum = nullptr; P.plan_tiles = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr; P.head_f16 = nullptr;
+    P.accum = nullptr; P.touched = nullptr; P.plan_tiles = nullptr; P.grad_bev = nullptr; P.grad_head = nullptr; P.head_f16 = nullptr;
     P.bev_layout = d->bev_layout;
     P.pillars = static_cast<long long>(d->bev_x) * d->bev_y;
     P.grid = make_grid_params(*d);
@@ -223,33 +223,21 @@ FIERY_API int fiery_lift_plan(const fiery_lift_desc_t* desc, const float* calib_
     const PlanView v = plan_view(plan_out, P.n_frames, P.n_cameras, P.n_wtiles, P.pillars, 0);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     FIERY_CUDA_CHECK(cudaMemsetAsync(const_cast<unsigned char*>(v.touched), 0, static_cast<size_t>(P.n_frames) * P.pillars, st));
-    return launch_lift_plan(P, const_cast<unsigned char*>(v.tiles), const_cast<unsigned char*>(v.touched), st);
+    return launch_lift_plan(P, const_cast<unsigned char*>(v.tiles), const_cast<unsigned char*>(v.touched), 1, st);
 }
 
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* d) {
     LiftParams P;
     if (!shape_params(d, P) || P.n_frames == 0) return 0;
-    const size_t chunk = static_cast<size_t>(lift_chunk_frames(P));
-    size_t accum_frame = 0;
-    const size_t frame = lift_scratch_frame_bytes(P, &accum_frame);
-    const size_t zeroed = (chunk * accum_frame + 127) & ~static_cast<size_t>(127);
-    return zeroed + chunk * (frame - accum_frame);
-}
-
-FIERY_API size_t fiery_lift_scratch_zeroed_bytes(const fiery_lift_desc_t* d) {
-    LiftParams P;
-    if (!shape_params(d, P) || P.n_frames == 0) return 0;
-    size_t accum_frame = 0;
-    lift_scratch_frame_bytes(P, &accum_frame);
-    return (static_cast<size_t>(lift_chunk_frames(P)) * accum_frame + 127) & ~static_cast<size_t>(127);
+    return lift_scratch_bytes(P);
 }
 
 FIERY_API void fiery_lift_set_max_chunk_frames(int32_t n) { lift_set_max_chunk_frames(n); }
 
-FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* d, int32_t has_plan) {
+FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* d) {
     LiftParams P;
     if (!shape_params(d, P) || P.n_frames == 0) return 0;
-    return lift_forward_launches(P, has_plan ? 1 : 0);
+    return lift_forward_launches(P);
 }
 
 FIERY_API size_t fiery_lift_workspace_bytes(const fiery_lift_desc_t* d) {

@@ -153,7 +153,7 @@ __device__ __forceinline__ void softmax_rows(const LiftParams& P, float* s_prob,
 }
 
 // MAXR: rows per thread the row loop is unrolled for (ceil(h / 4) <= MAXR); the g_ctx accumulators take 8 registers per row
-template <int MAXR>
+template <int MAXR, bool LDS_EARLY>
 __global__ void __launch_bounds__(BW_NT, 3)
 lift_backward_kernel(const __grid_constant__ HeadMapsCols head_maps, const __grid_constant__ HeadMapsCols grad_maps, const LiftParams P) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -218,12 +218,24 @@ lift_backward_kernel(const __grid_constant__ HeadMapsCols head_maps, const __gri
     }
     if (R > 0) {
 #pragma unroll
-        for (int j = 0; j < BW_ND; ++j) {                           // prime: G <- run 0, Gn <- run 1, pnn <- pillar of run 2
+        for (int j = 0; j < BW_ND; ++j) {                           // prime: Gn <- run 0, pnn <- pillar of run 1
             pnn[j] = __ldg(streams + sp[j]);
             ++sp[j];
             advance_slot(G[j], Gn[j], pnn[j], sp[j], gbev, streams, 1u);
-            advance_slot(G[j], Gn[j], pnn[j], sp[j], gbev, streams, 1u);
         }
+        float ps[BW_ND] = {0.f, 0.f, 0.f, 0.f};                    // g_prob partial sums of the previous row (reduced one row late)
+        // transposing butterfly over the 8 channel lanes: 4 values -> 1 per lane, summed over all 8 lanes.  It runs one row
+        // behind the FMAs (its three dependent shuffles hide under the next row's arithmetic).
+        auto reduce_and_store = [&](const float (&v4)[BW_ND], int off) {
+            const float send0 = b2 ? v4[0] : v4[2], keep0 = b2 ? v4[2] : v4[0];
+            const float send1 = b2 ? v4[1] : v4[3], keep1 = b2 ? v4[3] : v4[1];
+            const float a0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 4);
+            const float a1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 4);
+            const float send = b1 ? a0 : a1, keep = b1 ? a1 : a0;
+            float v = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            if (!(cl & 1)) s_gprob[off + jsel * WT] = v;
+        };
         for (int g = 0; g < BW_NG; ++g) {
             unsigned cm[BW_ND], anyj[BW_ND];
             unsigned anyrow = 0;
@@ -233,29 +245,40 @@ lift_backward_kernel(const __grid_constant__ HeadMapsCols head_maps, const __gri
                 anyj[j] = __reduce_or_sync(0xffffffffu, cm[j]);                // ... where any column of the warp does
                 anyrow |= anyj[j];
             }
-            if (g > 0) {                                            // the first run of the new depth group
+            // the first run of the depth group (g = 0 takes the same path: the primed rows move from Gn to G here)
 #pragma unroll
-                for (int j = 0; j < BW_ND; ++j) advance_slot(G[j], Gn[j], pnn[j], sp[j], gbev, streams, 1u);
-            }
+            for (int j = 0; j < BW_ND; ++j) advance_slot(G[j], Gn[j], pnn[j], sp[j], gbev, streams, 1u);
 #pragma unroll
             for (int i = 0; i < MAXR; ++i) {
                 if (i < R) {
                     const int h = r_lo + i;
+                    // operands of this row first: the shared loads are in flight while the run changes are handled
+                    const float* pr = s_prob + (h * BW_DPAD + g * BW_ND) * WT + col;
+                    const float* cx = s_ctx + h * 64 * WT + cl * WT + col;
+                    // LDS_EARLY: operands of the row are requested before the run changes are handled (more registers live)
+                    float pv[BW_ND];
+                    unsigned long long cp[4];
+                    if (LDS_EARLY) {
+#pragma unroll
+                        for (int j = 0; j < BW_ND; ++j) pv[j] = pr[j * WT];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) cp[m] = pack2(cx[(2 * m) * 8 * WT], cx[(2 * m + 1) * 8 * WT]);
+                    }
                     if (i > 0 && ((anyrow >> h) & 1u)) {            // warp-uniform: some slot of some column changes pillar here
 #pragma unroll
                         for (int j = 0; j < BW_ND; ++j)
                             if ((anyj[j] >> h) & 1u) advance_slot(G[j], Gn[j], pnn[j], sp[j], gbev, streams, (cm[j] >> h) & 1u);
                     }
-                    const float* pr = s_prob + (h * BW_DPAD + g * BW_ND) * WT + col;
-                    const float* cx = s_ctx + h * 64 * WT + cl * WT + col;
-                    unsigned long long cp[4];
+                    if (!LDS_EARLY) {
 #pragma unroll
-                    for (int m = 0; m < 4; ++m) cp[m] = pack2(cx[(2 * m) * 8 * WT], cx[(2 * m + 1) * 8 * WT]);
+                        for (int j = 0; j < BW_ND; ++j) pv[j] = pr[j * WT];
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) cp[m] = pack2(cx[(2 * m) * 8 * WT], cx[(2 * m + 1) * 8 * WT]);
+                    }
                     float sj[BW_ND];
 #pragma unroll
                     for (int j = 0; j < BW_ND; ++j) {
-                        const float pv = pr[j * WT];
-                        const unsigned long long pp = pack2(pv, pv);
+                        const unsigned long long pp = pack2(pv[j], pv[j]);
 #pragma unroll
                         for (int m = 0; m < 4; ++m) fma2_acc(gc[i][m], pp, G[j][m]);          // g_ctx += prob * G
                         unsigned long long t = mul2(cp[0], G[j][0]);                          // ctx . G over my 8 channels
@@ -267,18 +290,14 @@ lift_backward_kernel(const __grid_constant__ HeadMapsCols head_maps, const __gri
                         sj[j] = lo + hi;
                     }
                     if (P.use_depth) {
-                        // transposing butterfly over the 8 channel lanes: 4 values -> 1 per lane, summed over all 8 lanes
-                        const float send0 = b2 ? sj[0] : sj[2], keep0 = b2 ? sj[2] : sj[0];
-                        const float send1 = b2 ? sj[1] : sj[3], keep1 = b2 ? sj[3] : sj[1];
-                        const float a0 = keep0 + __shfl_xor_sync(0xffffffffu, send0, 4);
-                        const float a1 = keep1 + __shfl_xor_sync(0xffffffffu, send1, 4);
-                        const float send = b1 ? a0 : a1, keep = b1 ? a1 : a0;
-                        float v = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        if (!(cl & 1)) s_gprob[(h * BW_DPAD + g * BW_ND + jsel) * WT + col] = v;
+                        if (i > 0) reduce_and_store(ps, ((h - 1) * BW_DPAD + g * BW_ND) * WT + col);   // the previous row's g_prob
+#pragma unroll
+                        for (int j = 0; j < BW_ND; ++j) ps[j] = sj[j];
                     }
                 }
             }
+            // the last row of the group: its shuffles overlap with the set-up of the next depth group
+            if (P.use_depth) reduce_and_store(ps, ((r_lo + R - 1) * BW_DPAD + g * BW_ND) * WT + col);
         }
     }
     // ---- g_ctx registers -> the ctx region, same layout (every thread overwrites exactly the entries only it read) -------------------
@@ -351,7 +370,7 @@ nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int 
     }
 }
 
-int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, cudaStream_t stream);
+int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, int want_streams, cudaStream_t stream);
 
 size_t lift_backward_relayout_bytes(const LiftParams& P) {
     return P.bev_layout == FIERY_BEV_NCHW ? static_cast<size_t>(P.n_frames) * P.pillars * P.C * sizeof(float) : 0;
@@ -381,13 +400,20 @@ int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, 
         Q.plan_tiles = plan_view(plan, P.n_frames, P.n_cameras, P.n_wtiles, P.pillars, 0).tiles;
     } else {                                          // no plan from the forward: compute the geometry here
         FIERY_REQUIRE(workspace != nullptr, "backward without a plan needs the workspace of fiery_lift_workspace_bytes()");
-        rc = launch_lift_plan(Q, ws, nullptr, stream);
+        rc = launch_lift_plan(Q, ws, nullptr, 1, stream);
         if (rc != FIERY_OK) return rc;
         Q.plan_tiles = ws;
     }
     const BwdLayout L(P.hh);
     FIERY_REQUIRE(L.total <= 227 * 1024, "tile needs %d bytes of shared memory", L.total);
     const bool small = (P.hh + PLAN_RG - 1) / PLAN_RG <= 7;     // the reference's h = 28: 7 rows per thread
+    bool early = false;
+#ifdef FIERY_COLS_AB
+    if (const char* e = getenv("FIERY_BWD_EARLY")) early = atoi(e) != 0;      // A/B builds only
+#endif
+    typedef void (*kernel_t)(const HeadMapsCols, const HeadMapsCols, const LiftParams);
+    const kernel_t variants[4] = {lift_backward_kernel<7, false>, lift_backward_kernel<7, true>,
+                                  lift_backward_kernel<BW_MAXR, false>, lift_backward_kernel<BW_MAXR, true>};
     {
         static std::mutex mu;
         static std::atomic<int> configured_on[64];    // function attributes are per device; zero-initialised
@@ -397,19 +423,16 @@ int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, 
         if (!configured.load(std::memory_order_acquire)) {
             std::lock_guard<std::mutex> lock(mu);
             if (!configured.load(std::memory_order_relaxed)) {
-                FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_backward_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_backward_kernel<7>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                      cudaSharedmemCarveoutMaxShared));
-                FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_backward_kernel<BW_MAXR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_backward_kernel<BW_MAXR>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                      cudaSharedmemCarveoutMaxShared));
+                for (kernel_t k : variants) {
+                    FIERY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    FIERY_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                }
                 configured.store(1, std::memory_order_release);
             }
         }
     }
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
-    if (small) lift_backward_kernel<7><<<static_cast<unsigned>(n_tiles), BW_NT, L.total, stream>>>(hm, gm, Q);
-    else lift_backward_kernel<BW_MAXR><<<static_cast<unsigned>(n_tiles), BW_NT, L.total, stream>>>(hm, gm, Q);
+    variants[(small ? 0 : 2) + (early ? 1 : 0)]<<<static_cast<unsigned>(n_tiles), BW_NT, L.total, stream>>>(hm, gm, Q);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }

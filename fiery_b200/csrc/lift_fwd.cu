@@ -66,10 +66,6 @@ finalize_nchw_kernel(float* __restrict__ accum, unsigned char* __restrict__ flag
 constexpr int FT_P = 64;
 constexpr int FT_THREADS = 256;
 
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
 __device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes) : "memory");
 }
@@ -197,19 +193,12 @@ __global__ void compose_calibration_kernel(int n, const float* __restrict__ K, c
 // ---------------------------------------------------------------------------------------------------------------------
 // Frames per launch.  Measured on B200 (profiles/r01_notes.md): chunks small enough to keep the accumulator L2-resident (3 frames,
 // 31 MB) are slower end to end (152.9 us vs 122.7 us for 9 frames) -- the extra launches and the single-wave grids cost more than the
-// saved HBM traffic -- so the chunk only bounds the scratch footprint (1 GiB: accumulator + marks + plan records of a chunk).
-static std::atomic<int> g_max_chunk_frames{0};       // fiery_lift_set_max_chunk_frames (test hook: forces the multi-chunk path)
+// saved HBM traffic -- so the chunk only bounds the scratch footprint (1 GiB: accumulator + marks of a chunk).
+static std::atomic<int> g_max_chunk_frames{0};       // fiery_lift_set_max_chunk_frames (test hook: forces the multi-pass path)
 void lift_set_max_chunk_frames(int n) { g_max_chunk_frames.store(n > 0 ? n : 0); }
 
-size_t lift_scratch_frame_bytes(const LiftParams& P, size_t* accum_bytes_out) {
-    const size_t tiles = static_cast<size_t>(P.n_cameras) * P.n_wtiles * PLAN_TILE_BYTES;
-    const size_t accum = P.bev_layout == FIERY_BEV_NCHW ? static_cast<size_t>(P.pillars) * P.C * 4 + static_cast<size_t>(P.pillars) : 0;
-    if (accum_bytes_out) *accum_bytes_out = accum;
-    return accum + tiles;
-}
-
 int lift_chunk_frames(const LiftParams& P) {
-    const long long per_frame = static_cast<long long>(lift_scratch_frame_bytes(P, nullptr));
+    const long long per_frame = P.pillars * P.C * 4 + P.pillars;
     long long c = (1ll << 30) / (per_frame > 0 ? per_frame : 1);
     const int forced = g_max_chunk_frames.load();
     if (forced > 0 && forced < c) c = forced;
@@ -217,29 +206,14 @@ int lift_chunk_frames(const LiftParams& P) {
     return static_cast<int>(c < 1 ? 1 : c);
 }
 
-// scratch of one chunk: [accumulator (chunk, X*Y, C) fp32][marks (chunk, X*Y) bytes, padded to 128][plan tile records of the chunk]
-struct ScratchParts {
-    float* accum;
-    unsigned char* marks;
-    unsigned char* tiles;
-    size_t zeroed_bytes, total_bytes;
-};
-ScratchParts lift_scratch_parts(const LiftParams& P, void* scratch, int chunk) {
-    ScratchParts s;
-    const bool nchw = P.bev_layout == FIERY_BEV_NCHW;
-    const size_t acc = nchw ? static_cast<size_t>(chunk) * P.pillars * P.C * 4 : 0;
-    const size_t marks = nchw ? ((static_cast<size_t>(chunk) * P.pillars + 127) & ~static_cast<size_t>(127)) : 0;
-    unsigned char* base = static_cast<unsigned char*>(scratch);
-    s.accum = reinterpret_cast<float*>(base);
-    s.marks = base + acc;
-    s.tiles = base + acc + marks;
-    s.zeroed_bytes = acc + marks;
-    s.total_bytes = acc + marks + static_cast<size_t>(chunk) * P.n_cameras * P.n_wtiles * PLAN_TILE_BYTES;
-    return s;
+// scratch of one pass (NCHW output): [accumulator (chunk, X*Y, C) fp32][marks (chunk, X*Y) bytes, padded to 128]; all zero between calls
+size_t lift_scratch_bytes(const LiftParams& P) {
+    if (P.bev_layout != FIERY_BEV_NCHW || P.n_frames <= 0) return 0;
+    const size_t chunk = static_cast<size_t>(lift_chunk_frames(P));
+    return chunk * P.pillars * P.C * 4 + ((chunk * P.pillars + 127) & ~static_cast<size_t>(127));
 }
 
 int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stream);
-int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, cudaStream_t stream);
 int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels, int n_frames, int box_pillars);
 
 // Side streams and fork/join events of the forward chains: created once per host thread and device (thread_local, so concurrent
@@ -289,9 +263,9 @@ int lift_forward_groups(const LiftParams& P, int frames_in_chunk) {
 }
 
 // kernel launches of one forward call (include/fiery_b200.h: fiery_lift_forward_launches)
-int lift_forward_launches(const LiftParams& P, int has_plan) {
+int lift_forward_launches(const LiftParams& P) {
     if (P.n_frames <= 0) return 0;
-    const int per_group = (has_plan ? 0 : 1) + 1 + (P.bev_layout == FIERY_BEV_NCHW ? 1 : 0);
+    const int per_group = 1 + (P.bev_layout == FIERY_BEV_NCHW ? 1 : 0);
     const int chunk = lift_chunk_frames(P);
     int n = 0;
     for (int f0 = 0; f0 < P.n_frames; f0 += chunk)
@@ -324,7 +298,7 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     FIERY_REQUIRE(P.ww % 4 == 0, "feat_w=%d must be a multiple of 4 (TMA row pitch must be 16-byte aligned)", P.ww);
     FIERY_REQUIRE(P.hh <= PLAN_MAX_ROWS, "feat_h=%d not supported by this build (<= %d)", P.hh, PLAN_MAX_ROWS);
     const bool nchw = P.bev_layout == FIERY_BEV_NCHW;
-    FIERY_REQUIRE(scratch != nullptr || (!nchw && plan != nullptr), "the scratch buffer of fiery_lift_scratch_bytes() is required");
+    FIERY_REQUIRE(scratch != nullptr || !nchw, "NCHW output needs the zeroed scratch buffer of fiery_lift_scratch_bytes()");
     int rc = FIERY_OK;
     LiftParams Q = P;
     Q.head_f16 = head_dtype == FIERY_DTYPE_F16 ? head : nullptr;
@@ -332,11 +306,11 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     if (const char* e = getenv("FIERY_CHAINS")) g_max_chains = atoi(e) < MAX_CHAINS ? atoi(e) : MAX_CHAINS;
     if (const char* e = getenv("FIERY_CHAIN_MIN_TILES")) g_chain_min_tiles = atoi(e);
 #endif
-    // lift into a channel-last accumulator (NHWC: the caller's zero-filled output itself), then the layout pass for NCHW; chunked
-    // only to bound the scratch footprint
+    // lift into a channel-last accumulator (NHWC: the caller's zero-filled output itself), then the layout pass for NCHW; several
+    // passes only to bound the scratch footprint
     const int chunk = lift_chunk_frames(P);
-    const ScratchParts sp = lift_scratch_parts(P, scratch, chunk);
-    const size_t tiles_per_frame = static_cast<size_t>(P.n_cameras) * P.n_wtiles;
+    float* accum = static_cast<float*>(scratch);    // [accumulator floats of one pass][one mark byte per pillar]
+    unsigned char* scratch_marks = nchw ? reinterpret_cast<unsigned char*>(accum + static_cast<size_t>(chunk) * P.pillars * P.C) : nullptr;
     const bool tma_pass = P.pillars % 4 == 0;      // the output map needs a 16-byte row pitch
     CUtensorMap bev_map;
     if (nchw && tma_pass) {
@@ -364,20 +338,17 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
             Q.frame0 = f0 + s0;
             Q.n_frames = s1 - s0;
             unsigned char* marks = nullptr;         // "pillar receives a point" bytes the layout pass reads
-            if (plan) {                             // caller-owned plan of the whole batch: read only
+            if (plan) {                             // caller-owned plan of the whole batch: read only, marks included
                 const PlanView v = plan_view(plan, P.n_frames, P.n_cameras, P.n_wtiles, P.pillars, Q.frame0);
                 Q.plan_tiles = v.tiles;
+                Q.touched = nullptr;
                 marks = const_cast<unsigned char*>(v.touched);
-            } else {                                // geometry of this group, into the scratch
-                unsigned char* tiles = sp.tiles + static_cast<size_t>(s0) * tiles_per_frame * PLAN_TILE_BYTES;
-                marks = nchw ? sp.marks + static_cast<size_t>(s0) * P.pillars : nullptr;
-                timer_begin(st, 0);
-                rc = launch_lift_plan(Q, tiles, marks, st);
-                timer_end(st);
-                if (rc != FIERY_OK) return rc;
-                Q.plan_tiles = tiles;
+            } else {                                // the tile kernel evaluates the geometry itself and marks into the scratch
+                Q.plan_tiles = nullptr;
+                marks = nchw ? scratch_marks + static_cast<size_t>(s0) * P.pillars : nullptr;
+                Q.touched = marks;
             }
-            Q.accum = nchw ? sp.accum + static_cast<size_t>(s0) * P.pillars * P.C
+            Q.accum = nchw ? accum + static_cast<size_t>(s0) * P.pillars * P.C
                            : bev_out + static_cast<size_t>(Q.frame0) * P.pillars * P.C;
             timer_begin(st, 1);
             rc = launch_forward_cols(Q, head, st);

@@ -32,6 +32,8 @@ namespace fiery {
 constexpr int COLS_DPAD = 48;                 // depth slots (D <= 48)
 constexpr int COLS_NPAIR = COLS_DPAD * WT;    // (depth, column) pairs of a tile: each is one image column of points
 constexpr int COLS_EVS = 33;                  // event words per unit: rows 0..31 + one that stays 0
+constexpr int COLS_PLAN_STAGE = 4096;         // bytes of the tile's plan record staged in shared memory by one bulk copy ...
+constexpr int COLS_RUNS_STAGED = (COLS_PLAN_STAGE - PLAN_OFF_RUNS) / 4;   // ... = header + this many runs; later runs are read from global
 // A "unit" is DD adjacent depths x the 4 columns of the tile (4*DD pairs = "slots"); the 64 / CPL lanes of a unit own CPL
 // channels each.  DD trades shared-memory traffic for registers: per image row a unit reads the whole 1 KB context row of the
 // tile, so the tile's context traffic is (48 / DD) KB per row.
@@ -43,10 +45,11 @@ struct HeadMapsCols {
 
 struct ColsLayout {
     int hh, C;
-    int off_bar, off_ev, off_prob, off_ctx, off_pillar, total;
+    int off_bar, off_plan, off_ev, off_prob, off_ctx, off_pillar, total;
     __host__ __device__ ColsLayout(int hh_, int C_, int n_units) : hh(hh_), C(C_) {
         int o = 0;
-        off_bar = o;    o += 16;
+        off_bar = o;    o += 16;                        // two mbarriers: head tile, plan record
+        off_plan = o;   o += COLS_PLAN_STAGE;           // head of the tile's plan record: masks, offsets, the first runs
         off_ev = o;     o += n_units * COLS_EVS * 4;   // run-end events: [unit][row], see expand_plan
         o = (o + 127) & ~127;
         off_prob = o;   o += hh * COLS_DPAD * WT * 4;
@@ -100,23 +103,112 @@ __device__ __forceinline__ void expand_plan(const ColsLayout& L, unsigned char* 
     static_assert(NT >= COLS_NPAIR, "one thread per (depth, column) pair at least");
     const int pair = threadIdx.x;
     if (pair >= COLS_NPAIR) return;
+    const unsigned char* staged = smem + L.off_plan;
     int* tab = reinterpret_cast<int*>(smem + L.off_pillar) + pair;
-    unsigned m = __ldg(reinterpret_cast<const unsigned*>(rec + PLAN_OFF_MASK) + pair);
-    const int* runs = reinterpret_cast<const int*>(rec + PLAN_OFF_RUNS) + __ldg(reinterpret_cast<const unsigned short*>(rec + PLAN_OFF_OFF) + pair);
+    unsigned m = reinterpret_cast<const unsigned*>(staged + PLAN_OFF_MASK)[pair];
+    int k = reinterpret_cast<const unsigned short*>(staged + PLAN_OFF_OFF)[pair];
+    const int* s_runs = reinterpret_cast<const int*>(staged + PLAN_OFF_RUNS);
+    const int* g_runs = reinterpret_cast<const int*>(rec + PLAN_OFF_RUNS);
+    auto run = [&](int idx) { return idx < COLS_RUNS_STAGED ? s_runs[idx] : __ldg(g_runs + idx); };
     const int d = pair >> 2, col = pair & 3;
     const int j = (d % DD) * 4 + col;
     unsigned* ev = reinterpret_cast<unsigned*>(smem + L.off_ev) + (d / DD) * COLS_EVS;
-    int cur = __ldg(runs);
+    int cur = run(k);
     while (m) {
         const int h = __ffs(m) - 1;                       // rows h-1 | h lie in different pillars
         m &= m - 1;
-        const int nxt = __ldg(++runs);
+        const int nxt = run(++k);
         atomicOr(ev + h, (1u << j) | (cur >= 0 ? (1u << (4 * DD + j)) : 0u));
         if (cur >= 0) tab[(h - 1) * COLS_NPAIR] = cur;
         cur = nxt;
     }
     tab[(L.hh - 1) * COLS_NPAIR] = cur;                   // the run that reaches the last row
 }
+
+// constants of the in-tile geometry live where a planned tile stages its plan record
+constexpr int GEO_OFF_CAM = 0, GEO_OFF_U = 48, GEO_OFF_V = 64, GEO_OFF_D = 192;
+
+// Calls WITHOUT a plan (a forward-only call whose calibration is new: nothing to share the geometry with): the geometry of the tile
+// is evaluated here, while the head tile is in flight -- the tile kernel waits for the copy engine at that point anyway, so this
+// costs no time (measured on B200: tile kernel 49-51 us for 8 frames with or without it), whereas a separate plan kernel in front of
+// every frame group does (step 81.6 vs 71.4 us).  Same device functions as the plan kernel (geometry.cuh), same result:
+// the pillar (rank, fiery.py:236-256; -1 = masked) of every point, evaluated with the reference arithmetic, reduced on the fly to
+// what the pooling loop consumes:
+//   ev[unit][row]      bit j (slot j = dd*4 + col: depth DD*unit + dd, column col) set <=> pair j changes pillar between
+//                      row-1 and row; bit 4*DD + j: ... and the run that ends sits on a valid pillar (it must be flushed, the
+//                      others are only cleared)
+//   pillar[row][pair]  written only where it is read: the last row of every run
+//   touched[pillar]    the layout pass's map of pillars that receive something, marked at every run start
+// thread = (pair, row range); the NRS ranges of a pair sit in adjacent lanes and hand their last pillar to the next range.
+template <bool POW2, int NT, int DD>
+__device__ __forceinline__ void stage_geometry_cols(const LiftParams& P, const ColsLayout& L, unsigned char* smem, int w0,
+                                                    unsigned char* touched) {
+    constexpr int NRS = NT / COLS_NPAIR >= 4 ? 4 : (NT / COLS_NPAIR >= 2 ? 2 : 1);
+    static_assert(NT >= COLS_NPAIR, "one thread per (depth, column) pair at least");
+    const float* s_cam = reinterpret_cast<const float*>(smem + L.off_plan + GEO_OFF_CAM);
+    const float* s_u = reinterpret_cast<const float*>(smem + L.off_plan + GEO_OFF_U);
+    const float* s_v = reinterpret_cast<const float*>(smem + L.off_plan + GEO_OFF_V);
+    const float* s_d = reinterpret_cast<const float*>(smem + L.off_plan + GEO_OFF_D);
+    int* s_pillar = reinterpret_cast<int*>(smem + L.off_pillar);
+    unsigned* s_ev = reinterpret_cast<unsigned*>(smem + L.off_ev);
+    CameraTransform T;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) T.m[i] = s_cam[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) T.t[i] = s_cam[9 + i];
+    const float offx = P.grid.off[0], offy = P.grid.off[1], offz = P.grid.off[2];
+    const float kx = POW2 ? P.grid.inv_res[0] : P.grid.res[0], ky = POW2 ? P.grid.inv_res[1] : P.grid.res[1];
+    const float Xf = static_cast<float>(P.grid.X), Yf = static_cast<float>(P.grid.Y);
+    const float z_lo = P.grid.z_lo, z_hi = P.grid.z_hi;
+    const int Y = P.grid.Y;
+    const int hh = L.hh;
+    const int pair = threadIdx.x / NRS, rs = threadIdx.x % NRS;
+    const bool idle = pair >= COLS_NPAIR;                    // NT is not always a multiple of the pair count
+    const int d = idle ? 0 : pair >> 2, col = pair & 3;
+    const int unit = d / DD, j = (d % DD) * 4 + col;
+    const bool split = hh >= 2 * NRS;                       // short columns: one lane of the pair walks all rows
+    const int h_lo = idle ? 0 : (split ? (hh * rs) / NRS : 0);
+    const int h_hi = idle ? 0 : (split ? (hh * (rs + 1)) / NRS : (rs == 0 ? hh : 0));
+    const bool dead = d >= P.D || w0 + col >= P.ww;
+
+    unsigned* ev = s_ev + unit * COLS_EVS;
+    int* tab = s_pillar + (idle ? 0 : pair);
+    auto run_ends = [&](int h, int before, int now) {        // rows h-1 | h lie in different pillars
+        atomicOr(ev + h, (1u << j) | (before >= 0 ? (1u << (4 * DD + j)) : 0u));
+        if (before >= 0) tab[(h - 1) * COLS_NPAIR] = before;
+        if (touched && now >= 0) touched[now] = 1;          // the layout pass gathers only marked pillars
+    };
+
+    int first = -1, prev = -1;
+    if (!dead && h_lo < h_hi) {
+        const float depth = s_d[d];
+        const ColumnTerms ct = column_terms(T, s_u[col], depth);
+        int h = h_lo;
+#pragma unroll 2
+        for (; h < h_hi; ++h) {
+            float p[3];
+            ego_point(T, ct, s_v[h], depth, p);                               // fiery.py:199-205
+            const float ax = __fsub_rn(p[0], offx), ay = __fsub_rn(p[1], offy), az = __fsub_rn(p[2], offz);
+            const float sx = POW2 ? __fmul_rn(ax, kx) : __fdiv_rn(ax, kx);    // fiery.py:236 (x scale exact when res is 2^k)
+            const float sy = POW2 ? __fmul_rn(ay, ky) : __fdiv_rn(ay, ky);
+            const int rank = static_cast<int>(sx) * Y + static_cast<int>(sy); // truncation, fiery.py:237,252-256
+            const int cur = select_pillar(sx, sy, az, Xf, Yf, z_lo, z_hi, rank);   // mask, fiery.py:240-247
+            if (h == h_lo) first = cur;
+            else if (cur != prev) run_ends(h, prev, cur);
+            prev = cur;
+        }
+    }
+    const int before = __shfl_up_sync(0xffffffffu, prev, 1);   // last pillar of the previous row range of this pair
+    if (h_lo < h_hi) {
+        if (rs > 0 && split) {
+            if (first != before) run_ends(h_lo, before, first);
+        } else if (touched && first >= 0) {
+            touched[first] = 1;                                     // row 0 starts a run
+        }
+        if (h_hi == hh) tab[(hh - 1) * COLS_NPAIR] = prev;          // the run that reaches the last row
+    }
+}
+
 
 // ---- half-precision head tensors (AMP: Encoder.depth_layer emits fp16, encoder.py:96 under PRECISION 16) ------------------------
 // The row pitch of an fp16 plane (w * 2 bytes) is not a multiple of 16 for the reference's w = 60, so the tensor maps cannot
@@ -270,7 +362,7 @@ __device__ __forceinline__ void flush_depth(unsigned long long (&acc)[CPL][DD][2
 
 // CPL channels per lane, DD depths per unit: a unit is 64 / CPL lanes, a tile 48 / DD units.
 //   CPL 2, DD 2: 768 threads (a unit is a warp)      CPL 2, DD 4: 384 threads      CPL 4, DD 4: 192 threads (a unit is a half-warp)
-template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false>
+template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false, bool PLANNED = false>
 __global__ void __launch_bounds__((COLS_DPAD / DD) * (64 / CPL), MINB)
 lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const LiftParams P) {
     constexpr int LPU = 64 / CPL;                     // lanes per unit
@@ -290,13 +382,21 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
     // (img_local indexes the plan's tile records and the accumulator; img the head tensor)
 
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    const unsigned char* rec = PLANNED ? P.plan_tiles + static_cast<size_t>(blockIdx.x) * PLAN_TILE_BYTES : nullptr;
+    if (tid == 0) {
+        if (PLANNED) mbar_init(bar + 1, 1);
+        if (!HALF) mbar_init(bar, 1);
+        fence_mbar_init();
+        if (PLANNED) {                                // the tile's geometry: head of its plan record, one bulk copy
+            mbar_arrive_expect_tx(bar + 1, COLS_PLAN_STAGE);
+            bulk_load_1d(smem + L.off_plan, rec, COLS_PLAN_STAGE, bar + 1);
+        }
+    }
     if (HALF) {
         issue_half_tile<CPL, NT>(P, L, smem, img, w0);
     } else if (tid == 0) {
         tma_prefetch_desc(&head_maps.depth);
         tma_prefetch_desc(&head_maps.ctx);
-        mbar_init(bar, 1);
-        fence_mbar_init();
         const uint32_t prob_bytes = P.use_depth ? static_cast<uint32_t>(hh * COLS_DPAD * WT * 4) : 0u;
         mbar_arrive_expect_tx(bar, prob_bytes + static_cast<uint32_t>(hh * L.C * WT * 4));
         if (P.use_depth) tma_load_4d(smem + L.off_prob, &head_maps.depth, bar, w0, 0, 0, img);
@@ -306,9 +406,33 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
         unsigned* s_ev = reinterpret_cast<unsigned*>(smem + L.off_ev);
         for (int i = tid; i < NU * COLS_EVS; i += NT) s_ev[i] = 0u;
     }
-    __syncthreads();                                  // event words cleared, the mbarrier is set up
-    // geometry of the tile: the runs the plan kernel computed for it (the head tile stays in flight meanwhile)
-    expand_plan<NT, DD>(L, smem, P.plan_tiles + static_cast<size_t>(blockIdx.x) * PLAN_TILE_BYTES);
+    if (!PLANNED) {                                   // constants of the in-tile geometry; one lane composes R @ K^-1 (fiery.py:203)
+        float* s_u = reinterpret_cast<float*>(smem + L.off_plan + GEO_OFF_U);
+        float* s_v = reinterpret_cast<float*>(smem + L.off_plan + GEO_OFF_V);
+        float* s_d = reinterpret_cast<float*>(smem + L.off_plan + GEO_OFF_D);
+        if (tid < WT) s_u[tid] = (w0 + tid < P.ww) ? P.fu[w0 + tid] : 0.f;
+        if (tid >= 32 && tid < 64) s_v[tid - 32] = P.fv[min(tid - 32, hh - 1)];
+        if (tid >= 64 && tid < 64 + COLS_DPAD) s_d[tid - 64] = (tid - 64 < P.D) ? P.fd[tid - 64] : 0.f;
+        if (tid == NT - 1) {
+            CameraTransform T;
+            load_camera(P.calib_mode, P.calib_a, P.calib_b, img, T);
+            float* s_cam = reinterpret_cast<float*>(smem + L.off_plan + GEO_OFF_CAM);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) s_cam[i] = T.m[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) s_cam[9 + i] = T.t[i];
+        }
+    }
+    __syncthreads();                                  // event words cleared, constants and the mbarriers are set up
+    // geometry of the tile (the head tile stays in flight meanwhile): the runs of its plan record, or evaluated here
+    if (PLANNED) {
+        if (tid < COLS_NPAIR) mbar_wait(bar + 1, 0);
+        expand_plan<NT, DD>(L, smem, rec);
+    } else {
+        unsigned char* touched = P.touched ? P.touched + static_cast<size_t>(frame) * P.pillars : nullptr;
+        if (P.grid.pow2[0] && P.grid.pow2[1]) stage_geometry_cols<true, NT, DD>(P, L, smem, w0, touched);
+        else stage_geometry_cols<false, NT, DD>(P, L, smem, w0, touched);
+    }
     if (HALF) widen_half_tile<NT>(P, L, smem);         // fp16 pieces -> the fp32 tile, in place
     else mbar_wait(bar, 0);                           // head tile has landed
     softmax_cols<NT>(P, L, smem);
@@ -371,21 +495,19 @@ lift_forward_cols_kernel(const __grid_constant__ HeadMapsCols head_maps, const L
 
 int encode_head_maps_cols(HeadMapsCols* maps, const void* head, const LiftParams& P, int channels_per_lane);
 
-template <int CPL, int DD, int MINB, int UNR = 2, bool HALF = false>
+template <int CPL, int DD, int MINB, int UNR, bool HALF, bool PLANNED>
 static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStream_t stream) {
     constexpr int NU = COLS_DPAD / DD, NT = NU * (64 / CPL);
     const ColsLayout L(P.hh, P.C, NU);
-    static bool configured_on[64] = {};              // function attributes are per device
-    int dev_id = 0;
-    FIERY_CUDA_CHECK(cudaGetDevice(&dev_id));
-    bool& configured = configured_on[dev_id & 63];
-    if (!configured) {
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        // ask for the full shared-memory carve-out (3 x 74 KB per SM for the reference shape)
-        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    static OncePerDevice once;                        // zero-initialised (static storage)
+    int rc = once.run([]() -> int {
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PLANNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        // ask for the full shared-memory carve-out (two or three tiles of ~75 KB per SM for the reference shape)
+        FIERY_CUDA_CHECK(cudaFuncSetAttribute(lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PLANNED>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                               cudaSharedmemCarveoutMaxShared));
-        configured = true;
-    }
+        return FIERY_OK;
+    });
+    if (rc != FIERY_OK) return rc;
     FIERY_REQUIRE(L.total <= 227 * 1024, "tile needs %d bytes of shared memory", L.total);
     HeadMapsCols maps;
     if (HALF) {
@@ -393,50 +515,43 @@ static int launch_forward_cols_t(const LiftParams& P, const void* head, cudaStre
         FIERY_REQUIRE(P.head_f16 != nullptr && (reinterpret_cast<uintptr_t>(P.head_f16) & 7) == 0,
                       "half-precision head tensor must be 8-byte aligned");
     } else {
-        const int rc = encode_head_maps_cols(&maps, head, P, CPL);
+        rc = encode_head_maps_cols(&maps, head, P, CPL);
         if (rc != FIERY_OK) return rc;
     }
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
-    lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
+    lift_forward_cols_kernel<CPL, DD, MINB, UNR, HALF, PLANNED><<<static_cast<unsigned>(n_tiles), NT, L.total, stream>>>(maps, P);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }
 
-// Measured on B200, 8 frames (profiles/r01_notes.md).  The pooling loop is bound by shared-memory wavefronts (a broadcast
-// LDS.128 costs 2, a 512-byte one 4) and the rest of the tile by instruction issue, so the shape of a unit is a trade between
-// context re-reads (48 / DD per row), registers (4 * CPL * DD accumulators) and resident warps.
+// Unit shape (CPL channels per lane, DD depths per unit), measured on B200.  The pooling loop is bound by shared-memory wavefronts
+// (a broadcast LDS.128 costs 2, a 512-byte one 4) and by the run-end control flow, so the shape trades context re-reads (48 / DD per
+// row), registers (4 * CPL * DD accumulators) and resident warps.  CPL 4 and DD 4 shapes lose (profiles/r01_notes.md,
+// profiles/r02_notes.md).
+//   * geometry in the tile (no plan): DD = 3 (512 threads, 57 registers) is 7-8 % faster when the grid fills whole waves of 2 tiles
+//     per SM (9 frames: 55.3 vs 60.2 us); DD = 2 (768 threads, row loop not unrolled) is faster while tiles run alone on an SM, i.e.
+//     when the last wave is at most half full (8 frames: 51.1 vs 53.4 us);
+//   * geometry from a plan: DD = 3 always (8 frames: 49.2 vs 53.3 us, 9 frames: 51.1 vs 55.4 us).
 int launch_forward_cols(const LiftParams& P, const void* head, cudaStream_t stream) {
     FIERY_REQUIRE(P.hh <= 32, "feat_h=%d not supported by this build (<= 32)", P.hh);
     FIERY_REQUIRE(P.C == 64 && P.D <= COLS_DPAD, "column kernel: C=%d D=%d not supported", P.C, P.D);
-    // Unit shape, measured on B200 (profiles/r01_notes.md): DD = 3 (512 threads, 58 registers) is 7-8 % faster when the grid fills
-    // whole waves of 2 tiles per SM (9 frames: 55.3 vs 60.2 us, 12 frames at 400x200: 72.0 vs 77.1 us); DD = 2 (768 threads) is
-    // faster while tiles run alone on an SM, i.e. when the last wave is at most half full (8 frames: 52.3 vs 53.4 us; its row
-    // loop is not unrolled: 51.1 vs 52.3 us with two rows per trip, 56.4 us with four -- 40 registers leave no room).
+    const bool planned = P.plan_tiles != nullptr;
     int n_sm = 0, dev = 0;
     FIERY_CUDA_CHECK(cudaGetDevice(&dev));
     FIERY_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
     const long long rem = n_tiles % (2ll * n_sm);
-    int variant = (rem > 0 && rem <= n_sm) ? 0 : 2;
+    bool dd3 = planned || !(rem > 0 && rem <= n_sm);
 #ifdef FIERY_COLS_AB
-    // A/B builds only (tools/gpu_ab.sh): unit shape chosen per call
-    if (const char* e = getenv("FIERY_COLS_VARIANT")) variant = atoi(e) >= 0 ? atoi(e) : variant;
-    switch (variant) {
-        case 1: return launch_forward_cols_t<2, 4, 2>(P, head, stream);
-        case 4: return launch_forward_cols_t<4, 4, 3>(P, head, stream);
-        case 5: return launch_forward_cols_t<4, 2, 3>(P, head, stream);
-        case 6: return launch_forward_cols_t<4, 3, 3>(P, head, stream);
-        case 7: return launch_forward_cols_t<2, 4, 3>(P, head, stream);
-        case 8: return launch_forward_cols_t<2, 2, 2, 2>(P, head, stream);
-        default: break;
-    }
+    if (const char* e = getenv("FIERY_COLS_VARIANT")) dd3 = atoi(e) < 0 ? dd3 : atoi(e) == 2;      // A/B builds only: 0 = DD 2, 2 = DD 3
 #endif
-    if (P.head_f16) {
-        if (variant == 2) return launch_forward_cols_t<2, 3, 2, 2, true>(P, head, stream);
-        return launch_forward_cols_t<2, 2, 2, 1, true>(P, head, stream);
+    const bool half = P.head_f16 != nullptr;
+    if (planned) {
+        if (dd3) return half ? launch_forward_cols_t<2, 3, 2, 2, true, true>(P, head, stream) : launch_forward_cols_t<2, 3, 2, 2, false, true>(P, head, stream);
+        return half ? launch_forward_cols_t<2, 2, 2, 1, true, true>(P, head, stream) : launch_forward_cols_t<2, 2, 2, 1, false, true>(P, head, stream);
     }
-    if (variant == 2) return launch_forward_cols_t<2, 3, 2>(P, head, stream);
-    return launch_forward_cols_t<2, 2, 2, 1>(P, head, stream);
+    if (dd3) return half ? launch_forward_cols_t<2, 3, 2, 2, true, false>(P, head, stream) : launch_forward_cols_t<2, 3, 2, 2, false, false>(P, head, stream);
+    return half ? launch_forward_cols_t<2, 2, 2, 1, true, false>(P, head, stream) : launch_forward_cols_t<2, 2, 2, 1, false, false>(P, head, stream);
 }
 
 }  // namespace fiery

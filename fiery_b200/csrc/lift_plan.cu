@@ -9,15 +9,14 @@ namespace fiery {
 
 template <bool POW2>
 __global__ void __launch_bounds__(PLAN_PAIRS)
-lift_plan_kernel(const LiftParams P, unsigned char* __restrict__ tiles, unsigned char* __restrict__ touched) {
+lift_plan_kernel(const LiftParams P, unsigned char* __restrict__ tiles, unsigned char* __restrict__ touched, int want_streams) {
     __shared__ float s_cam[12];
     __shared__ float s_u[WT];
     __shared__ float s_v[PLAN_MAX_ROWS];
     __shared__ float s_d[48];
     __shared__ unsigned s_mask[PLAN_PAIRS];
     __shared__ int s_warp_sum[PLAN_PAIRS / 32];
-    __shared__ int s_len[PLAN_STREAMS];
-    __shared__ int s_soff[PLAN_STREAMS + 1];
+    __shared__ unsigned short s_seg[PLAN_RG * PLAN_PAIRS];   // segment lengths, then offsets, in (rg, col, j, g) order
     __shared__ int s_tmp[PLAN_MAX_ROWS * PLAN_PAIRS];     // [k][pair]: pillar of the pair's k-th run
 
     const int tid = threadIdx.x;
@@ -106,56 +105,73 @@ lift_plan_kernel(const LiftParams P, unsigned char* __restrict__ tiles, unsigned
         for (int k = 0; k < n; ++k) runs[k] = s_tmp[k * PLAN_PAIRS + pair];
     }
 
-    // ---- backward streams: per (row group, column, slot j) the runs of depths j, 4 + j, 8 + j, ... clipped to the row group ---------
-    const int s = tid;
-    const int rg = s >> 4, scol = (s >> 2) & 3, sj = s & 3;
-    const int r_lo = plan_group_row(hh, rg & (PLAN_RG - 1)), r_hi = plan_group_row(hh, (rg & (PLAN_RG - 1)) + 1);
-    const unsigned upto_lo = (2u << r_lo) - 1u;                                 // rows 0 .. r_lo
-    const unsigned upto_hi = r_hi >= 32 ? 0xffffffffu : ((1u << r_hi) - 1u);    // rows 0 .. r_hi - 1
-    if (s < PLAN_STREAMS) {
-        int len = 2;                                                            // two pad entries
-        for (int g = 0; g < 48 / PLAN_ND; ++g) {
-            const unsigned m = s_mask[((g * PLAN_ND + sj) << 2) + scol];
-            len += 1 + __popc(m & upto_hi & ~upto_lo);
-        }
-        s_len[s] = len;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int i = 0; i < PLAN_STREAMS; ++i) { s_soff[i] = acc; acc += s_len[i]; }
-        s_soff[PLAN_STREAMS] = acc;
-    }
     if (tid == PLAN_PAIRS - 1) reinterpret_cast<unsigned*>(rec + PLAN_OFF_COUNTS)[0] = static_cast<unsigned>(base + incl);   // n_runs
+    if (!want_streams) {                                 // forward-only plan: the backward streams are not built
+        if (tid == 0) reinterpret_cast<unsigned*>(rec + PLAN_OFF_COUNTS)[1] = 0u;
+        return;
+    }
+
+    // ---- backward streams: per (row group, column, slot j) the runs of depths j, 4 + j, 8 + j, ... clipped to the row group --------
+    // A segment = the runs of one pair inside one row group: the run that contains the group's first row + the runs that start
+    // inside the group.  Stream (rg, col, j) = segments of depth groups g = 0..11 in order + two pad entries; the streams follow each
+    // other in streams[].  Offsets: exclusive scan over the 768 segment lengths in (rg, col, j, g) order, + 2 per preceding stream.
+    constexpr int NG = 48 / PLAN_ND;
+    const int g_of = d / PLAN_ND, j_of = d % PLAN_ND;
+    unsigned in_group[PLAN_RG], upto[PLAN_RG];
+#pragma unroll
+    for (int rg = 0; rg < PLAN_RG; ++rg) {
+        const int r_lo = plan_group_row(hh, rg), r_hi = plan_group_row(hh, rg + 1);
+        upto[rg] = (2u << r_lo) - 1u;                                                   // rows 0 .. r_lo
+        in_group[rg] = (r_hi >= 32 ? 0xffffffffu : ((1u << r_hi) - 1u)) & ~upto[rg];    // rows r_lo + 1 .. r_hi - 1
+        s_seg[((rg * WT + col) * PLAN_ND + j_of) * NG + g_of] = static_cast<unsigned short>(1 + __popc(mask & in_group[rg]));
+    }
     __syncthreads();
-    if (s < PLAN_STREAMS) {
-        reinterpret_cast<unsigned short*>(rec + PLAN_OFF_SOFF)[s] = static_cast<unsigned short>(s_soff[s]);
-        int* out = reinterpret_cast<int*>(rec + PLAN_OFF_STREAMS) + s_soff[s];
-        for (int g = 0; g < 48 / PLAN_ND; ++g) {
-            const int p = ((g * PLAN_ND + sj) << 2) + scol;
-            const unsigned m = s_mask[p];
-            const int k0 = __popc(m & upto_lo);                                 // the run that contains row r_lo
-            const int c = __popc(m & upto_hi & ~upto_lo);                       // runs that start inside the group
-            for (int k = k0; k <= k0 + c; ++k) *out++ = s_tmp[k * PLAN_PAIRS + p];
+    {   // thread t scans the ordered entries 4t .. 4t+3 (one third of a stream), then warp / block prefix
+        const int e0 = tid * 4;
+        const int l0 = s_seg[e0], l1 = s_seg[e0 + 1], l2 = s_seg[e0 + 2], l3 = s_seg[e0 + 3];
+        int tot = l0 + l1 + l2 + l3, inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
         }
-        out[0] = -1;
-        out[1] = -1;
+        if (lane == 31) s_warp_sum[warp] = inc;       // (the run-count sums in s_warp_sum were consumed before the barrier above)
+        __syncthreads();
+        int sbase = 0;
+#pragma unroll
+        for (int w = 0; w < PLAN_PAIRS / 32; ++w) sbase += (w < warp) ? s_warp_sum[w] : 0;
+        const int ex = sbase + inc - tot + 2 * (e0 / NG);                               // + the pads of the streams before mine
+        s_seg[e0] = static_cast<unsigned short>(ex);
+        s_seg[e0 + 1] = static_cast<unsigned short>(ex + l0);
+        s_seg[e0 + 2] = static_cast<unsigned short>(ex + l0 + l1);
+        s_seg[e0 + 3] = static_cast<unsigned short>(ex + l0 + l1 + l2);
+        if (tid == PLAN_PAIRS - 1) reinterpret_cast<unsigned*>(rec + PLAN_OFF_COUNTS)[1] = static_cast<unsigned>(ex + tot + 2);   // n_stream
     }
-    if (tid == 0) {
-        unsigned* counts = reinterpret_cast<unsigned*>(rec + PLAN_OFF_COUNTS);
-        counts[1] = static_cast<unsigned>(s_soff[PLAN_STREAMS]);                // n_stream
+    __syncthreads();
+    int* streams = reinterpret_cast<int*>(rec + PLAN_OFF_STREAMS);
+#pragma unroll
+    for (int rg = 0; rg < PLAN_RG; ++rg) {
+        int pos = s_seg[((rg * WT + col) * PLAN_ND + j_of) * NG + g_of];
+        const int k0 = __popc(mask & upto[rg]);                                         // the run that contains row r_lo
+        const int c = __popc(mask & in_group[rg]);                                      // runs that start inside the group
+        for (int k = k0; k <= k0 + c; ++k) streams[pos++] = s_tmp[k * PLAN_PAIRS + pair];
+        if (g_of == NG - 1) {                                                           // last segment of its stream: the pads
+            streams[pos] = -1;
+            streams[pos + 1] = -1;
+        }
     }
+    if (tid < PLAN_STREAMS) reinterpret_cast<unsigned short*>(rec + PLAN_OFF_SOFF)[tid] = s_seg[tid * NG];
 }
 
-int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, cudaStream_t stream) {
+int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, int want_streams, cudaStream_t stream) {
     FIERY_REQUIRE(P.hh >= 1 && P.hh <= PLAN_MAX_ROWS, "feat_h=%d not supported by this build (<= %d)", P.hh, PLAN_MAX_ROWS);
     FIERY_REQUIRE(P.D >= 1 && P.D <= 48, "depth_bins=%d not supported by this build (1..48)", P.D);
     const long long n_tiles = static_cast<long long>(P.n_frames) * P.n_cameras * P.n_wtiles;
     if (n_tiles == 0) return FIERY_OK;
     if (P.grid.pow2[0] && P.grid.pow2[1])
-        lift_plan_kernel<true><<<static_cast<unsigned>(n_tiles), PLAN_PAIRS, 0, stream>>>(P, tiles, touched);
+        lift_plan_kernel<true><<<static_cast<unsigned>(n_tiles), PLAN_PAIRS, 0, stream>>>(P, tiles, touched, want_streams);
     else
-        lift_plan_kernel<false><<<static_cast<unsigned>(n_tiles), PLAN_PAIRS, 0, stream>>>(P, tiles, touched);
+        lift_plan_kernel<false><<<static_cast<unsigned>(n_tiles), PLAN_PAIRS, 0, stream>>>(P, tiles, touched, want_streams);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }

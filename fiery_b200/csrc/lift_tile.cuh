@@ -33,7 +33,8 @@ struct LiftParams {
     const float* fd;         // (D) frustum depth                     fiery.py:115
     const void* head_f16;    // forward, half-precision head tensor (fetched with cp.async; fp32 heads come through the tensor maps)
     float* accum;            // forward: (B', X*Y, C) channel-last accumulation target
-    const unsigned char* plan_tiles;    // geometry plan (lift_plan.cuh): tile records of this launch's first frame onwards
+    unsigned char* touched;  // forward without a plan, NCHW output: (B', X*Y) byte map of pillars that receive a point
+    const unsigned char* plan_tiles;    // geometry plan (lift_plan.cuh): tile records of this launch's first frame onwards, or NULL
     const float* grad_bev;   // backward: (B', X*Y, C) or (B', C, X*Y)
     float* grad_head;        // backward output
     int bev_layout;

@@ -364,10 +364,10 @@ class LiftSplat(nn.Module):
                 out = store
             if plan is not None and plan.numel() < int(lib.fiery_lift_plan_bytes(desc)):
                 raise ValueError("plan was made for another batch shape: rebuild it with LiftSplat.plan(intrinsics, extrinsics)")
-            if scratch is None and B:
+            if scratch is None and B and self.output_layout != "channels_last":
                 pooled = int(lib.fiery_lift_scratch_bytes(desc))
-                scratch = _scratch.get(dev, pooled)            # zero-filled once; the kernels keep its accumulator part zeroed
-            scratch_ptr = scratch.data_ptr() if B else 0
+                scratch = _scratch.get(dev, pooled)            # zero-filled once; the kernels leave it zeroed again
+            scratch_ptr = scratch.data_ptr() if (B and scratch is not None) else 0
             status = lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
                                             c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
                                             plan.data_ptr() if plan is not None else 0, _stream_ptr(dev))
@@ -423,10 +423,9 @@ class GraphedLift:
         c = module._constants(dev)
         B, n = intrinsics.shape[:2]
         self.scratch = None
-        if B:
-            layout = _lib.BEV_NHWC if module.output_layout == "channels_last" else _lib.BEV_NCHW
-            desc = module._desc(c, B, n, head.dtype, _lib.CALIB_RAW, layout)
-            self.scratch = torch.zeros(max(1, int(_lib.load().fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
+        if module.output_layout != "channels_last" and B:
+            desc = module._desc(c, B, n, head.dtype, _lib.CALIB_RAW, _lib.BEV_NCHW)
+            self.scratch = torch.zeros(int(_lib.load().fiery_lift_scratch_bytes(desc)) // 4, dtype=torch.float32, device=dev)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph), torch.no_grad():

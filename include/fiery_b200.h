@@ -90,25 +90,24 @@ FIERY_API const char* fiery_last_error(void);
 /*
  * Geometry plan.  Where every frustum point lands -- get_geometry (fiery.py:193-208) and the voxel index, mask and rank of
  * projection_to_birds_eye_view (fiery.py:236-256) -- depends on the calibration, the frustum and the BEV grid only, not on the head
- * tensor.  The plan kernel evaluates it once per batch (the reference's exact fp32 operation order) and stores it as pillar runs
- * per (camera, feature column, depth) plus one "receives a point" byte per pillar; forward and backward read it.
- * fiery_lift_forward / fiery_lift_backward take `plan`:
- *   NULL      the geometry is computed inside the call (into the scratch / workspace);
+ * tensor.  fiery_lift_plan evaluates it once for a batch of calibrations (the reference's exact fp32 operation order) and stores it
+ * as pillar runs per (camera, feature column, depth), in the orders the forward and the backward kernel consume, plus one "receives
+ * a point" byte per pillar.  fiery_lift_forward / fiery_lift_backward take `plan`:
+ *   NULL      the geometry is evaluated inside the call (forward: in the tile kernel, under the latency of its loads; backward: by
+ *             the plan kernel into the workspace);
  *   non-NULL  a buffer of fiery_lift_plan_bytes(desc) bytes filled by fiery_lift_plan with the SAME descriptor shape and the
- *             calibration of this batch -- e.g. the plan of the forward reused by its backward, or one plan reused by every call
- *             while the camera rig is static.  It is only read.
+ *             calibration of this batch -- the plan of a training step shared by its forward and backward, or one plan reused by
+ *             every call while the camera rig is static.  It is only read.
  */
 FIERY_API size_t fiery_lift_plan_bytes(const fiery_lift_desc_t* desc);
 FIERY_API int fiery_lift_plan(const fiery_lift_desc_t* desc, const float* calib_a, const float* calib_b, const float* frustum_u,
                               const float* frustum_v, const float* frustum_d, void* plan_out, void* stream);
 
-/* Bytes of device scratch fiery_lift_forward needs: for FIERY_BEV_NCHW output a channel-last fp32 accumulator (chunk, X*Y, C) and
- * one mark byte per pillar, followed by room for the plan records of one chunk (both layouts); chunk <= B' is the number of frames
- * processed per pass (all of them unless the scratch would exceed 1 GiB).
- * Invariant: the first fiery_lift_scratch_zeroed_bytes(desc) bytes (accumulator + marks; 0 for NHWC) must be all zero on entry;
- * they are all zero again when the call's work completes.  The rest is plain workspace. */
+/* Bytes of zero-initialised device scratch fiery_lift_forward needs for FIERY_BEV_NCHW output (0 for NHWC): a
+ * channel-last fp32 accumulator (chunk, X*Y, C) followed by one mark byte per pillar, where chunk <= B' is the number
+ * of frames processed per pass (all of them unless the accumulator would exceed 1 GiB).
+ * Invariant: the scratch must be all zero on entry; it is all zero again when the call's work completes. */
 FIERY_API size_t fiery_lift_scratch_bytes(const fiery_lift_desc_t* desc);
-FIERY_API size_t fiery_lift_scratch_zeroed_bytes(const fiery_lift_desc_t* desc);
 
 /*
  * Forward lift.  head: (B'*n, D+C, h, w) [C channels if !use_depth_distribution], dtype head_dtype (FIERY_DTYPE_F32, or
@@ -116,22 +115,21 @@ FIERY_API size_t fiery_lift_scratch_zeroed_bytes(const fiery_lift_desc_t* desc);
  * reference's softmax and outer product, encoder.py:99-100).
  * frustum_u (w), frustum_v (h), frustum_d (D): the separable factors of Fiery.frustum (fiery.py:109-128), fp32.
  * bev_out: (B',C,X,Y) fp32 in bev_layout.  For FIERY_BEV_NHWC the caller must pass bev_out zero-filled (the kernel
- * accumulates into it).  scratch: fiery_lift_scratch_bytes(desc) bytes (may be NULL for NHWC output with a caller-owned plan).
+ * accumulates into it) and scratch may be NULL.
  */
 FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                        const float* frustum_u, const float* frustum_v, const float* frustum_d,
                        float* bev_out, void* scratch, const void* plan, void* stream);
 
-/* Number of kernel launches one fiery_lift_forward call with this descriptor issues: per frame group the plan kernel (unless a
- * plan is passed), the tile kernel and, for NCHW, the layout pass; groups of frames run as concurrent chains on internal streams
- * that are forked from and joined back into `stream` with events, so the call behaves like work queued on `stream` and can be
- * captured in a graph. */
-FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* desc, int32_t has_plan);
+/* Number of kernel launches one fiery_lift_forward call with this descriptor issues (NHWC: the tile kernel; NCHW: tile kernel
+ * + layout pass per frame group; groups of frames run as concurrent chains on internal streams that are forked from and
+ * joined back into `stream` with events, so the call behaves like work queued on `stream` and can be captured in a graph). */
+FIERY_API int fiery_lift_forward_launches(const fiery_lift_desc_t* desc);
 
 /* fiery_lift_forward with every kernel launch bracketed by an event pair on its own stream (profiling / bench.py's roofline): runs
- * the call, synchronises `stream`, and writes per launch the duration in milliseconds and the kind (0 plan kernel, 1 tile kernel,
- * 2 layout pass) into host arrays of max_launches entries; *host_n_launches receives the count.  Launches of different chains
- * overlap, so the durations are what each kernel took while the others were running -- the launches the step really runs. */
+ * the call, synchronises `stream`, and writes per launch the duration in milliseconds and the kind (1 tile kernel, 2 layout pass)
+ * into host arrays of max_launches entries; *host_n_launches receives the count.  Launches of different chains overlap, so the
+ * durations are what each kernel took while the others were running -- the launches the step really runs. */
 FIERY_API int fiery_lift_forward_timed(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
                                        const float* frustum_u, const float* frustum_v, const float* frustum_d, float* bev_out,
                                        void* scratch, const void* plan, void* stream, int32_t max_launches, float* host_ms,

@@ -44,37 +44,34 @@ def test_argument_validation_without_gpu():
         d.bev_resolution[a] = 1.0
     rc = lib.fiery_lift_forward(d, 16, 16, 16, 16, 16, 16, 16, 16, None, None)
     assert rc == -1 and b"bev_z" in lib.fiery_last_error()
-    zeroed = 1 * 50 * 50 * 64 * 4 + 2560                       # accumulator + one mark byte per pillar (padded to 128)
-    assert lib.fiery_lift_scratch_zeroed_bytes(d) == zeroed
-    tiles = 1 * 1 * 4                                          # frames x cameras x column tiles (w = 16)
-    assert lib.fiery_lift_plan_bytes(d) == lib.fiery_lift_scratch_bytes(d) - zeroed + 2560     # tile records + touched map
-    assert (lib.fiery_lift_scratch_bytes(d) - zeroed) % tiles == 0
+    assert lib.fiery_lift_scratch_bytes(d) == 1 * 50 * 50 * 64 * 4 + 2560      # accumulator + one mark byte per pillar (padded to 128)
+    assert lib.fiery_lift_plan_bytes(d) > 4 * 1296 + 2560                       # 4 tile records (header + run lists) + touched map
+    assert lib.fiery_lift_workspace_bytes(d) >= 1 * 50 * 50 * 64 * 4           # NCHW gradient re-layout + room for a plan
     n = ctypes.c_int64(-1)
     assert lib.fiery_voxels_summing_plan(0, None, None, ctypes.byref(n), None) == 0 and n.value == 0
 
 
 def test_forward_launch_plan_without_gpu():
-    """fiery_lift_forward_launches is host logic: per frame group the plan kernel (unless a plan is passed), the tile kernel and,
-    for NCHW, the layout pass; a group holds at least one tile per SM (148), at most four groups per call, one for channel-last."""
+    """fiery_lift_forward_launches is host logic: one tile kernel for channel-last output; for NCHW one (tile kernel, layout
+    pass) chain per frame group, a group holding at least one tile per SM (148) and at most four groups per call."""
     lib = _lib.load()
     d = _lib.LiftDesc()
     d.n_cameras, d.depth_bins, d.channels, d.feat_h, d.feat_w = 6, 48, 64, 28, 60        # 90 tiles per frame
     d.bev_x, d.bev_y, d.bev_z = 200, 200, 1
     d.bev_layout = _lib.BEV_NCHW
-    groups = {0: 0, 1: 1, 2: 1, 3: 1, 4: 2, 5: 2, 6: 3, 8: 4, 9: 4, 12: 4, 60: 4, 100: 8}   # 100 frames: two passes (1 GiB of scratch each)
-    for frames, g in groups.items():
+    expect = {0: 0, 1: 2, 2: 2, 3: 2, 4: 4, 5: 4, 6: 6, 8: 8, 9: 8, 12: 8, 100: 8}
+    for frames, launches in expect.items():
         d.n_frames = frames
-        assert lib.fiery_lift_forward_launches(d, 0) == 3 * g, frames
-        assert lib.fiery_lift_forward_launches(d, 1) == 2 * g, frames
+        assert lib.fiery_lift_forward_launches(d) == launches, frames
     d.n_frames, d.bev_layout = 8, _lib.BEV_NHWC
-    assert lib.fiery_lift_forward_launches(d, 0) == 2 and lib.fiery_lift_forward_launches(d, 1) == 1
-    assert lib.fiery_lift_forward_launches(None, 0) == 0
+    assert lib.fiery_lift_forward_launches(d) == 1
+    assert lib.fiery_lift_forward_launches(None) == 0
     # the test hook that forces the multi-pass path: 8 frames in passes of 3, 3, 2 -> (1 + 1 + 1) groups
     d.bev_layout = _lib.BEV_NCHW
     lib.fiery_lift_set_max_chunk_frames(3)
     try:
-        assert lib.fiery_lift_forward_launches(d, 0) == 9
-        assert lib.fiery_lift_scratch_zeroed_bytes(d) == (3 * (200 * 200 * 64 * 4 + 200 * 200) + 127) // 128 * 128
+        assert lib.fiery_lift_forward_launches(d) == 6
+        assert lib.fiery_lift_scratch_bytes(d) == (3 * (200 * 200 * 64 * 4 + 200 * 200) + 127) // 128 * 128
     finally:
         lib.fiery_lift_set_max_chunk_frames(0)
 

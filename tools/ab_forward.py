@@ -37,11 +37,14 @@ def timed(fn, n=20):
     return float(np.mean(ts)) * 1e3, float(np.min(ts)) * 1e3
 
 
+PLAN = lift.plan(K_d, E_d)       # caller-owned plan: the timings below are the tile kernel (+ layout pass) alone
+
+
 def runner(layout, out, scratch):
     desc = lift._desc(c, F, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, layout)
     def run():
         _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
-                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), None, stream), "fwd")
+                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), PLAN.data_ptr(), stream), "fwd")
     return run, desc
 
 
@@ -86,7 +89,7 @@ for combo in combos:
     out_nchw.fill_(float("nan"))
     run(); torch.cuda.synchronize()
     err = float((out_nchw - ref_nchw).norm() / ref_nchw.norm())
-    clean = bool((scratch[:int(lib.fiery_lift_scratch_zeroed_bytes(desc)) // 4] == 0).all().item())
+    clean = bool((scratch == 0).all().item())
     for _ in range(3):
         run()
     mean, mn = timed(run)
@@ -97,7 +100,7 @@ for combo in combos:
         sp = s.cuda_stream
         def run_s():
             _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
-                                              c["d"].data_ptr(), out_nchw.data_ptr(), scratch.data_ptr(), None, sp), "fwd")
+                                              c["d"].data_ptr(), out_nchw.data_ptr(), scratch.data_ptr(), PLAN.data_ptr(), sp), "fwd")
         run_s(); torch.cuda.synchronize()
         with torch.cuda.graph(g, stream=s):
             run_s()
@@ -106,7 +109,7 @@ for combo in combos:
     gmean, gmn = timed(g.replay)
     torch.cuda.synchronize()
     err2 = float((out_nchw - ref_nchw).norm() / ref_nchw.norm())
-    clean2 = bool((scratch[:int(lib.fiery_lift_scratch_zeroed_bytes(desc)) // 4] == 0).all().item())
+    clean2 = bool((scratch == 0).all().item())
     # backward (eager, through the host layer: workspace allocation + re-layout + tile kernel)
     gh = lift._launch_backward(head, K_d, E_d, gout)
     if combo == combos[0]:
@@ -116,7 +119,7 @@ for combo in combos:
         lift._launch_backward(head, K_d, E_d, gout)
     bmean, bmn = timed(lambda: lift._launch_backward(head, K_d, E_d, gout))
     res["layout_pass"][combo] = {"us_mean": mean, "graph_us_mean": gmean, "graph_us_min": gmn, "rel_err": max(err, err2),
-                                 "scratch_clean": clean and clean2, "launches": int(lib.fiery_lift_forward_launches(desc, 0)),
+                                 "scratch_clean": clean and clean2, "launches": int(lib.fiery_lift_forward_launches(desc)),
                                  "bwd_us_mean": bmean, "bwd_rel_err_vs_first": berr}
     print("chains:min_tiles", combo, res["layout_pass"][combo], flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
