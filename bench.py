@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-from fiery_b200.synthetic import CONFIGS, LiftConfig, make_calibration, make_grad_bev, make_head
+from fiery_b200.synthetic import CONFIGS, LiftConfig, make_calibration, make_grad_bev, make_head  # noqa: F401
 
 METRIC = "camera->BEV lift frames/sec (6-cam 224x480 -> 200x200)"
 L2_FLUSH_BYTES = 256 << 20
@@ -102,8 +102,13 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_lift_once(oracle, head, K, E):
-    return oracle.lift(head, K, E)
+def cpu_lift_once(oracle, head, K, E, gout=None):
+    if gout is None:
+        with torch.no_grad():
+            return oracle.lift(head, K, E)
+    h = head.clone().requires_grad_(True)                     # forward + autograd backward to the head tensor
+    oracle.lift(h, K, E).backward(gout)
+    return h.grad
 
 
 def _best_thread_count(oracle, head, K, E, candidates):
@@ -122,7 +127,7 @@ def _best_thread_count(oracle, head, K, E, candidates):
     return best
 
 
-def time_cpu_reference(cfg: LiftConfig, frames: int, reps: int, warmup: int = 1):
+def time_cpu_reference(cfg: LiftConfig, frames: int, reps: int, warmup: int = 1, backward: bool = False):
     """Times the oracle's torch-CPU restatement of the reference op chain (fiery.py:193-273, encoder.py:99-100,
     geometry.py:283-314) on the host cores, at the thread count that is fastest on this box.
     Returns (frames_per_s, seconds_per_call, threads)."""
@@ -139,14 +144,14 @@ def time_cpu_reference(cfg: LiftConfig, frames: int, reps: int, warmup: int = 1)
     threads = _best_thread_count(O.LiftOracle.from_config(one), torch.from_numpy(make_head(one, seed=0)),
                                  torch.from_numpy(K1), torch.from_numpy(E1), cands)
     torch.set_num_threads(threads)
-    with torch.no_grad():
-        for _ in range(warmup):
-            cpu_lift_once(oracle, head, K, E)
-        ts = []
-        for _ in range(reps):
-            t0 = time.perf_counter()
-            cpu_lift_once(oracle, head, K, E)
-            ts.append(time.perf_counter() - t0)
+    gout = torch.from_numpy(make_grad_bev(sub, seed=0)) if backward else None
+    for _ in range(warmup):
+        cpu_lift_once(oracle, head, K, E, gout)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_lift_once(oracle, head, K, E, gout)
+        ts.append(time.perf_counter() - t0)
     sec = float(np.median(ts))
     return frames / sec, sec, threads
 
@@ -156,7 +161,7 @@ def config_dict(cfg: LiftConfig, args, world: int):
     X, Y = cfg.bev_hw
     return {"workload": cfg.name, "frames_per_step_per_gpu": cfg.frames, "n_cameras": cfg.n_cameras,
             "final_dim": list(cfg.final_dim), "feat_hw": list(cfg.feat_hw), "depth_bins": cfg.depth_bins,
-            "channels": cfg.out_channels, "bev": [X, Y], "direction": "forward", "output_layout": args.layout,
+            "channels": cfg.out_channels, "bev": [X, Y], "direction": args.direction, "output_layout": args.layout,
             "head_dtype": args.head_dtype}
 
 
@@ -165,7 +170,8 @@ def run_reference(args, cfg: LiftConfig, rank: int):
         return
     frames = cfg.frames                       # the same batch the GPU arm lifts per step
     steps = max(1, args.steps)
-    fps, sec, threads = time_cpu_reference(cfg, frames, reps=steps, warmup=max(1, min(args.warmup, 2)))
+    fps, sec, threads = time_cpu_reference(cfg, frames, reps=steps, warmup=max(1, min(args.warmup, 2)),
+                                           backward=(args.direction == "fwd_bwd"))
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -180,6 +186,131 @@ def run_reference(args, cfg: LiftConfig, rank: int):
     print(json.dumps(line), flush=True)
 
 
+# (batch, sequence) of the reference configs the workloads stand for: frames per step = batch x time receptive field
+BATCH_SEQ = {"cfg1_tiny": (1, 1), "cfg2_static_lss": (1, 1), "cfg2_static_lss_b8": (8, 1), "cfg3_baseline": (3, 3), "cfg4_pon": (4, 3),
+             "cfg6_res_0p4_0p3": (2, 1)}
+
+
+def run_train(args, cfg: LiftConfig, rank: int, local_rank: int, world: int):
+    """--direction fwd_bwd: one data-parallel training step per timed step (fiery_b200.train.LiftTrainer), weak scaling: every rank
+    trains on its own (batch x seq) samples of the global batch, ONE NCCL all-reduce of the flat gradient per step."""
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: fiery_b200 has no CPU path")
+    import torch.distributed as dist
+    from fiery_b200 import _lib, hostmem
+    from fiery_b200.train import LiftTrainer, synthetic_batch
+    _lib.load()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    numa = hostmem.bind_to_gpu_numa(local_rank, local_rank, 1)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    b, s = BATCH_SEQ[cfg.name]
+    frames = b * s
+    precision = 16 if args.head_dtype == "f16" else 32
+    trainer = LiftTrainer(cfg, dev, precision=precision, feature_input=True, seed=0)
+    batch = synthetic_batch(cfg, b, s, dev, seed=1000, feature_input=True, first_sample=rank * b)
+    host = {k: v.cpu().pin_memory() for k, v in batch.items()}
+    flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=dev)
+    W, S = max(args.warmup, 3), max(args.steps, 1)
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        ts = []
+        for _ in range(S):
+            flush.fill_(1.0)
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); e.record(); e.synchronize()
+            ts.append(a.elapsed_time(e))
+        return float(np.mean(ts))
+
+    def step_dev():
+        trainer.step(batch)
+
+    def step_e2e():                                   # the step's inputs come from pinned host memory, its loss goes back to the host
+        dev_batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return float(trainer.step(dev_batch))
+
+    for _ in range(W):
+        step_dev()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev = timed(step_dev)
+    barrier()
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ms_e2e = timed(step_e2e)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # the lift's share of the step: forward + backward through the autograd function alone, same tensors
+    head = trainer.model.encoder.depth_layer(batch["image"].reshape(frames * cfg.n_cameras, *batch["image"].shape[3:])).detach()
+    K_p, E_p = batch["intrinsics"].reshape(frames, cfg.n_cameras, 3, 3), batch["extrinsics"].reshape(frames, cfg.n_cameras, 4, 4)
+    X, Y = cfg.bev_hw
+    g_cl = torch.randn(frames, X, Y, cfg.out_channels, device=dev).permute(0, 3, 1, 2)
+    hg = head.clone().requires_grad_(True)
+
+    def lift_only():
+        hg.grad = None
+        trainer.model.lift(hg, K_p, E_p).backward(g_cl)
+    for _ in range(3):
+        lift_only()
+    ms_lift = timed(lift_only)
+
+    def reduce_max(x):
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    ms_dev, ms_e2e, ms_lift = reduce_max(ms_dev), reduce_max(ms_e2e), reduce_max(ms_lift)
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        total = frames * world
+        alg = (cfg.fwd_bytes_per_frame(4) + cfg.bwd_bytes_per_frame(4)) * frames
+        h2d = int(sum(v.numel() * v.element_size() for v in host.values()))
+        line = {
+            "metric": METRIC, "value": total / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": S, "warmup": W,
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": config_dict(cfg, args, world),          # identical in both arms
+            "details": {"batch_per_gpu": b, "time_receptive_field": s,
+                       "precision": precision, "step": "depth_layer (cuDNN, autocast) -> fused lift forward (channels-last BEV) -> BEV head "
+                       "+ uncertainty-weighted losses -> fused lift backward (shared geometry plan) -> ONE all-reduce of the flat fp32 "
+                       "gradient -> clip 5 -> Adam(3e-4, wd 1e-7); image backbone excluded (feature maps are the input)",
+                       "parallelism": f"dp{world}: batch sharded over {world} GPU(s), single NCCL all-reduce of {trainer.bucket.nbytes} gradient bytes per step",
+                       "l2": "flushed before every timed step (256 MiB write)",
+                       "host": {"numa_node": numa[0], "cores_bound": numa[1], "note": numa[2]},
+                       "timing": "CUDA events around the step, mean over steps, max over ranks"},
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": 3 * S,          # per step: lift_plan_kernel, lift_forward_cols_kernel, lift_backward_kernel
+            "lift_fwd_bwd": {"ms_per_step": ms_lift, "frames_per_s": total / (ms_lift * 1e-3),
+                             "what": "plan + lift forward + lift backward alone (autograd function, channels-last BEV and gradient)"},
+            "roofline": {"bound": "hbm", "kernel": "lift_plan_kernel + lift_forward_cols_kernel + lift_backward_kernel",
+                         "achieved": alg / (ms_lift * 1e-3) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                         "frac": alg / (ms_lift * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_step": alg,
+                         "how": "algorithmic bytes of lift forward + backward (SURVEY.md 8d) / time of the lift's autograd forward+backward"},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            fps, sec, threads = time_cpu_reference(cfg, min(frames, args.cpu_frames), reps=max(2, args.cpu_reps // 2), backward=True)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": f"forward+backward of the lift (oracle/lift_oracle.py through torch autograd) on "
+                                              f"{min(frames, args.cpu_frames)} frame(s) of {cfg.name}, {threads} threads"}
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -190,6 +321,10 @@ def main():
     # (single_timeframe.yml:8), the configuration the metric is quoted on; cfg3_baseline (9 frames) etc. via --workload
     ap.add_argument("--workload", default="cfg2_static_lss_b8", choices=sorted(CONFIGS))
     ap.add_argument("--layout", default="contiguous", choices=["contiguous", "channels_last"])
+    ap.add_argument("--direction", default="forward", choices=["forward", "fwd_bwd"],
+                    help="forward: the lift (the metric's definition).  fwd_bwd: the data-parallel TRAINING step around it "
+                         "(fiery_b200.train: depth_layer -> lift forward -> BEV head + losses -> lift backward -> ONE gradient "
+                         "all-reduce -> clip -> Adam), BASELINE.json configs[4] with --workload cfg3_baseline --head-dtype f16 --gpus 8")
     ap.add_argument("--head-dtype", default="f32", choices=["f32", "f16"],
                     help="dtype of the head tensor: f32 (the metric's definition) or f16 (AMP heads, baseline.yml PRECISION 16: the "
                          "forward tile kernel reads the half-precision tensor itself; all arithmetic stays fp32)")
@@ -206,6 +341,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, cfg, rank)
+        return
+    if args.direction == "fwd_bwd":
+        run_train(args, cfg, rank, local_rank, world)
         return
 
     if not torch.cuda.is_available():
@@ -464,14 +602,14 @@ def main():
             "value_eager": total_frames / (ms_eager * 1e-3), "ms_per_step_eager": ms_eager,
             "fwd_bwd": {"value": total_frames / (ms_fb * 1e-3), "unit": "frames/s", "ms_per_step": ms_fb,
                         "what": "LiftSplat.forward + autograd backward to the head tensor (eager; the plan is computed once and shared)"},
-            "config": {**config_dict(cfg, args, world),
-                       "parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
-                       "l2": "flushed before every timed step (256 MiB write); step time = CUDA events around the step",
-                       "api": "value: LiftSplat.capture() CUDA-graph replay (tile kernels incl. geometry + layout passes every step); "
-                              "value_static_rig: capture(static_calibration=True); value_eager: LiftSplat.forward; "
-                              "e2e: LiftSplat.lift_from_host (pinned host in/out, 3-stream chunk pipeline)",
-                       "host": {"numa_node": numa[0], "cores_bound": numa[1], "note": numa[2]},
-                       "timing": "mean over steps, max over ranks"},
+            "config": config_dict(cfg, args, world),          # identical in both arms
+            "details": {"parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
+                        "l2": "flushed before every timed step (256 MiB write); step time = CUDA events around the step",
+                        "api": "value: LiftSplat.capture() CUDA-graph replay (tile kernels incl. geometry + layout passes every step); "
+                               "value_static_rig: capture(static_calibration=True); value_eager: LiftSplat.forward; "
+                               "e2e: LiftSplat.lift_from_host (pinned host in/out, 3-stream chunk pipeline)",
+                        "host": {"numa_node": numa[0], "cores_bound": numa[1], "note": numa[2]},
+                        "timing": "mean over steps, max over ranks"},
             "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(head_h.numel() * head_h.element_size() + K_h.numel() * 4 + E_h.numel() * 4),
                     "d2h_bytes_per_step": int(out_h.numel() * 4)},

@@ -151,6 +151,9 @@ int launch_warp(int forward, int n_maps, int C, int H, int W, const float* a, lo
                 const unsigned char* copy_mask, float* b, long long b_stride, int nearest, cudaStream_t stream);
 int launch_warp_theta(int n_seq, int T, int cumulative, const float* flow, float ex, float ey, float* theta,
                       unsigned char* copy_mask, cudaStream_t stream);
+int launch_pack_conv_weights(const float* w_oihw, float* packed, cudaStream_t stream);
+int launch_bev_conv(int n_frames, int H, int W, const float* x_nhwc, const float* w_packed, const float* scale, const float* shift,
+                    int relu, float* y_nhwc, cudaStream_t stream);
 int vs_plan(int64_t n_rows, const int64_t* ranks, int32_t* seg, int64_t* host_n, cudaStream_t);
 int vs_forward(int64_t n_rows, int channels, int64_t feat_stride, const float* feats, const int64_t* coords,
                const int32_t* seg, int64_t n_seg, float* sums, int64_t* coords_out, cudaStream_t);
@@ -364,6 +367,17 @@ FIERY_API int fiery_warp_theta(int32_t n_sequences, int32_t T, int32_t cumulativ
     FIERY_REQUIRE(n_sequences == 0 || (flow && theta && (copy_mask || !cumulative)), "warp_theta: NULL pointer");
     return launch_warp_theta(n_sequences, T, cumulative ? 1 : 0, flow, spatial_extent_x, spatial_extent_y, theta, copy_mask,
                              static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_bev_conv_pack_weights(const float* weight_oihw, float* packed_out, void* stream) {
+    FIERY_REQUIRE(weight_oihw && packed_out, "bev conv: NULL weight pointer");
+    return launch_pack_conv_weights(weight_oihw, packed_out, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_bev_first_conv_forward(int32_t n_frames, int32_t height, int32_t width, const float* x_nhwc, const float* packed_weight,
+                                           const float* scale, const float* shift, int32_t relu, float* y_nhwc, void* stream) {
+    FIERY_REQUIRE(n_frames == 0 || (x_nhwc && packed_weight && y_nhwc), "bev conv: NULL pointer");
+    return launch_bev_conv(n_frames, height, width, x_nhwc, packed_weight, scale, shift, relu ? 1 : 0, y_nhwc, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -16,6 +16,8 @@
  *       exposes the integer voxel coordinates the reference computes at fiery.py:236-256 (for parity checks)
  *   fiery_compose_calibration
  *       exposes combined = R @ inverse(K), translation  (fiery.py:196,203)
+ *   fiery_bev_first_conv_forward
+ *       replaces Decoder.first_conv (+ bn1 + relu in eval mode)  fiery/models/decoder.py:11,59-61   [SURVEY.md section 8f, next-2]
  *   fiery_warp_features_forward / _backward, fiery_warp_theta
  *       replace affine_grid + grid_sample inside warp_features  fiery/utils/geometry.py:219-220 (called from
  *       cumulative_warp_features geometry.py:225-253, call site fiery.py:143)   [SURVEY.md section 8f, next-1]
@@ -207,6 +209,18 @@ FIERY_API int fiery_warp_features_backward(int32_t n_maps, int32_t channels, int
  */
 FIERY_API int fiery_warp_theta(int32_t n_sequences, int32_t T, int32_t cumulative, const float* flow, float spatial_extent_x,
                                float spatial_extent_y, float* theta, uint8_t* copy_mask, void* stream);
+
+/*
+ * First BEV convolution on the tensor cores (tcgen05, TF32 operands, fp32 accumulation in tensor memory) -- Decoder.first_conv
+ * (fiery/models/decoder.py:11,59): Conv2d(64, 64, kernel_size=7, stride=2, padding=3, bias=False), optionally followed by a per-channel
+ * affine (bn1 folded for inference, decoder.py:60) and relu (decoder.py:61).  [SURVEY.md section 8f, next-2]
+ * It consumes the lift's channel-last result directly: x_nhwc (B', H, W, 64) fp32 = FIERY_BEV_NHWC output of fiery_lift_forward;
+ * y_nhwc (B', Ho, Wo, 64) fp32 with Ho = (H - 1) / 2 + 1, Wo likewise.  packed_weight: (49, 64, 64) = (tap r*7+s, out, in), made from
+ * the module's (64, 64, 7, 7) weight by fiery_bev_conv_pack_weights.  scale / shift: 64 floats each, or both NULL.
+ */
+FIERY_API int fiery_bev_conv_pack_weights(const float* weight_oihw, float* packed_out, void* stream);
+FIERY_API int fiery_bev_first_conv_forward(int32_t n_frames, int32_t height, int32_t width, const float* x_nhwc, const float* packed_weight,
+                                           const float* scale, const float* shift, int32_t relu, float* y_nhwc, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,9 +1,10 @@
-"""CPU, world_size 2 over gloo: the batch x time sharding used for N > 1 GPUs.
+"""CPU, world_size 2 over gloo: the host-side logic of the N > 1 path.
 
-The lift has no parameters and no cross-frame dependency (fiery/models/fiery.py:231), so the multi-GPU path is:
-rank r lifts frames shard_frames(B', N, r); no collective on the data path; a training step all-reduces (averages) the
-gradients of whatever produced the head tensor, exactly once.  On this CPU box the per-rank compute is the oracle; the
-host-side logic under test (sharding, gather order, gradient averaging) is the same code path bench.py --gpus N uses.
+Frames are independent (fiery/models/fiery.py:231): rank r trains on the samples ``rank_shard`` gives it, there is no collective
+on the lift's data path, and a training step averages the gradients exactly once -- ``FlatGradBucket.all_reduce_mean``
+(fiery_b200/train.py), ONE all-reduce of one flat buffer.  Here the product's bucket, sharding and synthetic batch run over gloo on
+CPU tensors; the lift itself has no CPU path, so between the product's ``depth_layer`` and ``BevHead`` the oracle's lift stands in
+(the CUDA lift in the same harness is covered by tests/test_train_gpu.py).
 """
 import os
 import socket
@@ -13,8 +14,12 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from fiery_b200.synthetic import CONFIGS, LiftConfig, make_calibration, make_grad_bev, make_head, shard_frames
+from fiery_b200.synthetic import CONFIGS, LiftConfig
+from fiery_b200.train import BevHead, FlatGradBucket, StandInEncoder, rank_shard, synthetic_batch
 from oracle import lift_oracle as O
+
+CFG = LiftConfig(**{**CONFIGS["cfg1_tiny"].__dict__})
+GLOBAL_BATCH, SEQ = 4, 1
 
 
 def _free_port():
@@ -23,65 +28,77 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _inputs(frames):
-    cfg = LiftConfig(**{**CONFIGS["cfg1_tiny"].__dict__, "frames": frames})
-    K, E = make_calibration(cfg, seed=11)
-    return cfg, torch.from_numpy(K), torch.from_numpy(E), torch.from_numpy(make_head(cfg, seed=11)), \
-        torch.from_numpy(make_grad_bev(cfg, seed=11))
+class _CpuStandIn(torch.nn.Module):
+    """depth_layer -> (oracle lift) -> BevHead: the product's modules around the oracle's CPU lift."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(0)
+        self.encoder = StandInEncoder(CFG.depth_bins, CFG.out_channels)
+        self.head = BevHead(CFG.out_channels, width=8)
+
+    def forward(self, batch):
+        b, s, n = batch["image"].shape[:3]
+        feats = batch["image"].reshape(b * s * n, *batch["image"].shape[3:])
+        head = self.encoder.depth_layer(feats)
+        oracle = O.LiftOracle.from_config(LiftConfig(**{**CFG.__dict__, "frames": b * s}))
+        bev = oracle.lift(head, batch["intrinsics"].reshape(b * s, n, 3, 3), batch["extrinsics"].reshape(b * s, n, 4, 4))
+        out = self.head(bev)
+        return (out["instance_center"] - batch["centerness"].reshape(b * s, 1, *bev.shape[2:])).pow(2).mean()
 
 
-def _worker(rank, world, port, frames, out_q):
+def _grads(first, count):
+    model = _CpuStandIn()
+    bucket = FlatGradBucket(model.parameters())
+    batch = synthetic_batch(CFG, count, SEQ, torch.device("cpu"), seed=5, feature_input=True, first_sample=first)
+    model(batch).backward()
+    return bucket, batch
+
+
+def _worker(rank, world, port, out_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
-    cfg, K, E, head, gout = _inputs(frames)
-    mine = shard_frames(frames, world, rank)
-    n = cfg.n_cameras
-    sub = LiftConfig(**{**cfg.__dict__, "frames": len(mine)})
-    oracle = O.LiftOracle.from_config(sub)
-    sl = slice(mine.start, mine.stop)
-    # a stand-in for Encoder.depth_layer (1x1 conv, encoder.py:36): the only parameters upstream of the lift
-    torch.manual_seed(0)
-    w = torch.nn.Parameter(torch.randn(cfg.head_channels, cfg.head_channels) * 0.1)
-    feats = head[sl.start * n:sl.stop * n]
-    h = torch.einsum("oc,bchw->bohw", w, feats)
-    bev = oracle.lift(h, K[sl], E[sl])
-    loss = (bev * gout[sl]).sum() / frames                       # mean over the GLOBAL batch
-    loss.backward()
-    grad = w.grad.clone()
-    dist.all_reduce(grad, op=dist.ReduceOp.SUM)                  # the single gradient all-reduce of the step
-    gathered = [torch.zeros_like(bev) for _ in range(world)] if len(mine) * world == frames else None
-    if gathered is not None:
-        dist.all_gather(gathered, bev.detach())
+    first, count = rank_shard(GLOBAL_BATCH, world, rank)
+    bucket, batch = _grads(first, count)
+    n_calls = {"n": 0}
+    real = dist.all_reduce
+
+    def counting(*a, **k):
+        n_calls["n"] += 1
+        return real(*a, **k)
+    dist.all_reduce = counting
+    bucket.all_reduce_mean()                                     # the step's only collective
+    dist.all_reduce = real
     dist.barrier()
     if rank == 0:
         # numpy arrays travel by value; torch tensors would be shared through the producer's fd server, which dies with it
-        out_q.put((grad.numpy(), torch.cat(gathered).numpy() if gathered is not None else None))
+        out_q.put((bucket.flat.numpy().copy(), n_calls["n"], batch["image"].numpy().copy()))
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_sharding_matches_single_process():
-    frames, world = 4, 2
+def test_two_rank_flat_bucket_matches_single_process():
+    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, frames, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    grad, bev = q.get(timeout=240)
-    grad, bev = torch.from_numpy(grad), torch.from_numpy(bev)
+    flat, calls, image0 = q.get(timeout=240)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    # single-process reference on the whole batch
-    cfg, K, E, head, gout = _inputs(frames)
-    torch.manual_seed(0)
-    w = torch.nn.Parameter(torch.randn(cfg.head_channels, cfg.head_channels) * 0.1)
-    full = O.LiftOracle.from_config(cfg).lift(torch.einsum("oc,bchw->bohw", w, head), K, E)
-    ((full * gout).sum() / frames).backward()
-    assert torch.allclose(bev, full.detach(), rtol=1e-5, atol=1e-6)      # rank-major gather == batch order
-    assert torch.allclose(grad, w.grad, rtol=1e-4, atol=1e-6)            # summed shard grads == full-batch grad
+    assert calls == 1                                            # ONE all-reduce for all parameters
+    # single process on the whole global batch: mean over 4 samples == mean of the two ranks' means over 2 samples each
+    bucket, batch = _grads(0, GLOBAL_BATCH)
+    assert torch.allclose(torch.from_numpy(flat), bucket.flat, rtol=1e-4, atol=1e-7)
+    assert float(bucket.flat.abs().max()) > 0
+    # a rank's shard is the same rows of the global batch
+    first, count = rank_shard(GLOBAL_BATCH, world, 0)
+    assert torch.equal(torch.from_numpy(image0), batch["image"][first:first + count])
+    assert [rank_shard(7, 3, r) for r in range(3)] == [(0, 3), (3, 2), (5, 2)]
 
 
 def test_reference_arm_non_zero_ranks_exit_quietly():
