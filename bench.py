@@ -549,6 +549,37 @@ def main():
             warp_extra["reference_ops_on_gpu_ms"] = float(np.mean(t_wr))
         del out_w
 
+    # ---- next row: Decoder.first_conv 7x7 s2 64->64 on tcgen05, fed by the channel-last lift output ------
+    conv_extra = None
+    if rank == 0 and not args.no_extras:
+        from fiery_b200.bev_conv import first_conv_forward, pack_weight
+        xb = torch.randn(frames, X, Y, cfg.out_channels, device=dev).permute(0, 3, 1, 2)       # channels-last, like LiftSplat(channels_last)
+        wc = torch.randn(64, 64, 7, 7, device=dev) * 0.02
+        wp = pack_weight(wc)
+        with torch.no_grad():
+            for _ in range(3):
+                first_conv_forward(xb, wp)
+            c_ms = float(np.mean(timed_steps(lambda: first_conv_forward(xb, wp), S)))
+            old_tf32 = torch.backends.cudnn.allow_tf32
+            torch.backends.cudnn.allow_tf32 = True
+            for _ in range(3):
+                torch.nn.functional.conv2d(xb, wc, stride=2, padding=3)
+            l_ms = float(np.mean(timed_steps(lambda: torch.nn.functional.conv2d(xb, wc, stride=2, padding=3), S)))
+            torch.backends.cudnn.allow_tf32 = old_tf32
+        Ho, Wo = (X - 1) // 2 + 1, (Y - 1) // 2 + 1
+        flops = 2.0 * frames * Ho * Wo * 64 * 64 * 49
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                bf16_peak = float(json.load(fh)["bf16_tflops"])
+        except (OSError, ValueError, KeyError):
+            bf16_peak = 1590.0
+        conv_extra = {"frames": frames, "ms_per_call": c_ms, "tflops": flops / (c_ms * 1e-3) / 1e12, "flops": flops,
+                      "library_cudnn_tf32_ms": l_ms, "tf32_peak_tflops": bf16_peak / 2,
+                      "frac_of_tf32_peak": flops / (c_ms * 1e-3) / 1e12 / (bf16_peak / 2),
+                      "what": "fiery_b200.bev_conv.first_conv_forward (tcgen05 kind::tf32 implicit GEMM, TMA stride-2 im2col) on a "
+                              "channel-last (B', 200, 200, 64) fp32 BEV; peak = measured cuBLAS bf16 burst / 2 (TF32 runs at half the "
+                              "bf16 rate); library line: torch conv2d, cuDNN with allow_tf32, same tensors; L2 flushed before every call"}
+
     def reduce_max(x):
         if not distributed:
             return x
@@ -638,6 +669,8 @@ def main():
         }
         if vs_extra is not None:
             line["voxels_summing_dropin"] = vs_extra
+        if conv_extra is not None:
+            line["next_row_first_bev_conv"] = conv_extra
         if warp_extra is not None:
             warp_extra["frac_of_hbm_peak"] = warp_extra["achieved_gbs"] / peak
             line["next_row_cumulative_warp"] = warp_extra

@@ -15,8 +15,9 @@
 //             columns); tcgen05.commit releases the stage / signals the epilogue
 //   warps 2-5 epilogue: tcgen05.ld the 128 x 64 accumulator (one output pixel per thread), per-channel scale/shift (+ relu),
 //             16-byte stores into the channel-last output
-// Operands are the fp32 values read as TF32 (10-bit mantissa), accumulation fp32 -- what cuDNN does for this layer under torch's
-// default allow_tf32; the parity bar (tests/test_bev_conv_gpu.py) is stated against an fp64 convolution.
+// Operands are TF32 (10-bit mantissa: weights rounded when they are packed, activations read from fp32 by truncation), accumulation
+// fp32 -- the precision cuDNN uses for this layer under torch's default allow_tf32; the parity bar (tests/test_bev_conv_gpu.py) is
+// stated against an fp64 convolution: normwise < 1e-3 (measured 6-8e-4; cuDNN's TF32 path, which rounds both operands: 3e-4).
 #include "lift_plan.cuh"
 
 namespace fiery {
@@ -188,7 +189,11 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, float* __r
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= CV_TAPS * CV_C * CV_C) return;
     const int in = i % CV_C, out = (i / CV_C) % CV_C, tap = i / (CV_C * CV_C);
-    packed[i] = w[(static_cast<size_t>(out) * CV_C + in) * CV_TAPS + tap];
+    // rounded to TF32 (nearest, ties away) here, once per weight update: the tensor core would otherwise TRUNCATE the low mantissa
+    // bits of an fp32 operand.  (The activations stay as the lift wrote them -- a rounding pass over 82 MB is not worth 1.5e-4.)
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w[(static_cast<size_t>(out) * CV_C + in) * CV_TAPS + tap]));
+    packed[i] = __uint_as_float(r);
 }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

@@ -200,7 +200,11 @@ class LiftSplat(nn.Module):
         extrinsics (B', n, 4, 4) -> BEV features (B', C, X, Y) float32 (fiery.py:225-227 allocates float32).
         ``plan``: the geometry of this calibration from ``self.plan(intrinsics, extrinsics)`` -- pass it while the camera rig
         is static and the per-call geometry pass disappears; ``None`` computes it inside the call."""
-        return _LiftSplatFunction.apply(head, intrinsics, extrinsics, self, plan)
+        from . import ops
+        _require_cuda(head, "head")                     # loud and specific: the operators are registered for CUDA only
+        make_plan = plan is None and torch.is_grad_enabled() and head.requires_grad      # a training step shares one plan
+        bev, _plan = torch.ops.fiery_b200.lift_splat(head, intrinsics, extrinsics, plan, ops.register_module(self), make_plan)
+        return bev
 
     def plan(self, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:
         """The geometry plan of a batch of calibrations (fiery_lift_plan): where every frustum point lands -- get_geometry
@@ -434,36 +438,6 @@ class GraphedLift:
     def __call__(self) -> torch.Tensor:
         self.graph.replay()
         return self.output
-
-
-class _LiftSplatFunction(torch.autograd.Function):
-    """autograd node of the fused lift: saves the head tensor and the calibration (recomputing softmax and voxel indices
-    in backward is cheaper than saving the 124 MB/frame frustum volume the reference keeps alive)."""
-
-    @staticmethod
-    def forward(ctx, head, intrinsics, extrinsics, module: LiftSplat, plan=None):
-        # Under AMP (baseline.yml PRECISION 16) depth_layer emits fp16; the reference's softmax autocasts to fp32 and the
-        # fp32 x fp16 outer product promotes to fp32 (encoder.py:99-100), so the lift itself is fp32 there too.  The forward
-        # tile kernel can read the fp16 tensor itself (NATIVE_FP16_FORWARD); otherwise, and for bf16, the logits are widened
-        # on the device first.  The backward kernel always reads fp32.
-        ctx.head_dtype = head.dtype
-        native = head.dtype == torch.float32 or (head.dtype == torch.float16 and NATIVE_FP16_FORWARD)
-        head_in = head if native else head.float()
-        if plan is None and ctx.needs_input_grad[0] and intrinsics.shape[0]:
-            plan = module.plan(intrinsics.to(head.device), extrinsics)     # the geometry is computed once and shared with the backward
-        out = module._launch_forward(head_in, intrinsics, extrinsics, plan=plan)
-        ctx.module = module
-        ctx.plan = plan
-        ctx.save_for_backward(head_in, intrinsics, extrinsics)
-        return out
-
-    @staticmethod
-    def backward(ctx, grad_bev):
-        head, intrinsics, extrinsics = ctx.saved_tensors
-        if head.dtype != torch.float32:
-            head = head.float()                      # the backward kernel reads an fp32 head tensor
-        grad_head = ctx.module._launch_backward(head, intrinsics, extrinsics, grad_bev, plan=ctx.plan)
-        return grad_head.to(ctx.head_dtype), None, None, None, None     # calibration is data: no gradient (geometry.py:300)
 
 
 def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):

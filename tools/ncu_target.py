@@ -3,6 +3,7 @@
     python tools/ncu_target.py <workload> tile    # the column tile kernel alone (channel-last target), whole batch, 4 launches
     python tools/ncu_target.py <workload> step    # the NCHW step (tile kernels + layout passes of every frame group), 4 calls
     python tools/ncu_target.py <workload> bwd     # NCHW backward (re-layout + backward tile kernel), 3 calls
+    python tools/ncu_target.py <workload> conv    # the tcgen05 first BEV convolution on a channel-last BEV of the workload's size, 4 calls
 """
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -23,7 +24,13 @@ K_d, E_d = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
 lift = LiftSplat.from_config(cfg).to(dev)
 c = lift._constants(dev)
 X, Y = cfg.bev_hw
-if mode == "bwd":
+if mode == "conv":
+    from fiery_b200.bev_conv import first_conv_forward, pack_weight
+    xb = torch.randn(cfg.frames, X, Y, 64, device=dev).permute(0, 3, 1, 2)
+    wp = pack_weight(torch.randn(64, 64, 7, 7, device=dev) * 0.02)
+    for _ in range(4):
+        first_conv_forward(xb, wp)
+elif mode == "bwd":
     g = torch.from_numpy(make_grad_bev(cfg, seed=100)).to(dev)
     for _ in range(3):
         lift._launch_backward(head, K_d, E_d, g)
