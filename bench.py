@@ -662,7 +662,7 @@ def main():
                              "algorithmic_bytes_per_step": bwd_alg, "step_ms": ms_bwd,
                              "channels_last_grad": {"kernel": "lift_backward_kernel", "step_ms": ms_bwd_cl,
                                                     "achieved": gbs(bwd_alg, ms_bwd_cl), "frac": gbs(bwd_alg, ms_bwd_cl) / peak},
-                             "traffic": (load_traffic(cfg.name + "__bwd") or None),
+                             "traffic": (sum(load_traffic(cfg.name + "__bwd").values()) or None),
                              "how": "fiery_lift_backward with the forward's plan, eager C-ABI call, L2 flushed before every step; "
                                     "algorithmic bytes = read grad BEV + read head + write grad head (SURVEY.md 8d)"},
             "clocks": clocks,
