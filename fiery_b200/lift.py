@@ -203,7 +203,7 @@ class LiftSplat(nn.Module):
         from . import ops
         _require_cuda(head, "head")                     # loud and specific: the operators are registered for CUDA only
         make_plan = plan is None and torch.is_grad_enabled() and head.requires_grad      # a training step shares one plan
-        bev, _plan = torch.ops.fiery_b200.lift_splat(head, intrinsics, extrinsics, plan, ops.register_module(self), make_plan)
+        bev, _plan = torch.ops.fiery_b200.lift_splat(head, intrinsics, extrinsics, plan, ops.register_module(self, head.device), make_plan)
         return bev
 
     def plan(self, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:

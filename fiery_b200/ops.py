@@ -16,28 +16,25 @@ from typing import Optional, Tuple
 
 import torch
 
-_REGISTRY = {}          # handle -> weakref to the LiftSplat module
+_REGISTRY = {}          # handle -> (weakref to the LiftSplat module, (C, X, Y, channels_last) as python values for the fake impl)
 
 
-def register_module(module) -> int:
+def register_module(module, device: torch.device) -> int:
     handle = id(module)
-    if handle not in _REGISTRY or _REGISTRY[handle]() is not module:
-        _REGISTRY[handle] = weakref.ref(module, lambda _r, h=handle: _REGISTRY.pop(h, None))
+    X, Y, _ = module._constants(device)["dim"]                      # cached host-side integers: no device sync here
+    meta = (int(module.encoder_out_channels), int(X), int(Y), module.output_layout == "channels_last")
+    entry = _REGISTRY.get(handle)
+    if entry is None or entry[0]() is not module or entry[1] != meta:
+        _REGISTRY[handle] = (weakref.ref(module, lambda _r, h=handle: _REGISTRY.pop(h, None)), meta)
     return handle
 
 
 def _module(handle: int):
-    ref = _REGISTRY.get(handle)
-    m = ref() if ref is not None else None
+    entry = _REGISTRY.get(handle)
+    m = entry[0]() if entry is not None else None
     if m is None:
         raise RuntimeError("fiery_b200::lift_splat: the LiftSplat module behind this handle is gone")
     return m
-
-
-def _out_shape(handle: int, intrinsics: torch.Tensor):
-    m = _module(handle)
-    X, Y = int(m.bev_dimension[0]), int(m.bev_dimension[1])
-    return intrinsics.shape[0], m.encoder_out_channels, X, Y
 
 
 @torch.library.custom_op("fiery_b200::lift_splat", mutates_args=(), device_types="cuda")
@@ -58,8 +55,9 @@ def lift_splat(head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.T
 
 @lift_splat.register_fake
 def _(head, intrinsics, extrinsics, plan, handle, make_plan):
-    B, C, X, Y = _out_shape(handle, intrinsics)
-    bev = head.new_empty((B, X, Y, C), dtype=torch.float32).permute(0, 3, 1, 2) if _module(handle).output_layout == "channels_last" \
+    C, X, Y, channels_last = _REGISTRY[handle][1]                   # python values only: nothing here touches a real tensor
+    B = intrinsics.shape[0]
+    bev = head.new_empty((B, X, Y, C), dtype=torch.float32).permute(0, 3, 1, 2) if channels_last \
         else head.new_empty((B, C, X, Y), dtype=torch.float32)
     return bev, head.new_empty((0,), dtype=torch.uint8)
 

@@ -179,19 +179,25 @@ class LiftTrainer:
         self.scaler = torch.amp.GradScaler("cuda", enabled=(precision == 16))
         self.steps = 0
 
-    def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+    def forward_backward(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Forward, backward and the gradient exchange: afterwards ``bucket.flat`` holds the (loss-scaled) gradient averaged over
+        the data-parallel group."""
         self.bucket.zero()
         with torch.autocast("cuda", dtype=torch.float16, enabled=(self.precision == 16)):
             output = self.model(batch["image"], batch["intrinsics"], batch["extrinsics"])
             loss = self.model.loss(output, batch)
         self.scaler.scale(loss).backward()
         self.bucket.all_reduce_mean(self.group)                        # the step's only collective (scaled gradients: linear)
+        return loss.detach()
+
+    def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        loss = self.forward_backward(batch)
         self.scaler.unscale_(self.optimizer)
         torch.nn.utils.clip_grad_norm_(self.bucket.params, GRAD_NORM_CLIP)            # train.py:38 gradient_clip_val
         self.scaler.step(self.optimizer)
         self.scaler.update()
         self.steps += 1
-        return loss.detach()
+        return loss
 
 
 def rank_shard(global_batch: int, world_size: int, rank: int):

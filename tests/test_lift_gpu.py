@@ -421,7 +421,7 @@ def test_lift_is_a_dispatcher_operator():
     Kd, Ed = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
     head = torch.from_numpy(make_head(cfg, seed=3)).to(dev)
     lift = LiftSplat.from_config(cfg).to(dev)
-    handle = ops.register_module(lift)
+    handle = ops.register_module(lift, dev)
     h = head.clone().requires_grad_(True)
     bev, plan = torch.ops.fiery_b200.lift_splat(h, Kd, Ed, None, handle, True)
     assert plan.numel() > 0 and bev.grad_fn is not None and not plan.requires_grad
@@ -441,6 +441,6 @@ def test_lift_is_a_dispatcher_operator():
     assert O.normwise_error(out.detach().cpu(), O.LiftOracle.from_config(cfg).lift_exact(h16.detach().float().cpu(), torch.from_numpy(K),
                                                                                          torch.from_numpy(E))) < TOL
     # traceable: dynamo captures the call as ONE operator node (fake implementation gives shapes / dtypes)
-    fn = torch.compile(lambda x: lift(x, Kd, Ed) * 2.0, backend="eager", fullgraph=True)
+    fn = torch.compile(lambda x: torch.ops.fiery_b200.lift_splat(x, Kd, Ed, None, handle, False)[0] * 2.0, backend="eager", fullgraph=True)
     with torch.no_grad():
         assert O.normwise_error((fn(head) / 2.0).cpu(), bev.detach().cpu()) < 1e-6
