@@ -237,12 +237,14 @@ def run_train(args, cfg: LiftConfig, rank: int, local_rank: int, world: int):
         dev_batch = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         return float(trainer.step(dev_batch))
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:                                     # before the warm-up: see main()
+        sampler.start()
+        time.sleep(1.0)
+    barrier()
     for _ in range(W):
         step_dev()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ms_dev = timed(step_dev)
     barrier()
     for _ in range(2):
@@ -410,14 +412,18 @@ def main():
     graphed = lift.capture(head_d, K_d, E_d)
     graphed_static = lift.capture(head_d, K_d, E_d, static_calibration=True)
 
+    # the clock sampler (an nvidia-smi process) starts BEFORE the warm-up: its NVML start-up touches every GPU of the box and showed
+    # up as multi-millisecond outliers in the first timed steps of every rank at N = 8 (profiles/r02_notes.md)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(1.0)
+    barrier()
     for _ in range(W):
         graphed()
         graphed_static()
         step_eager()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     t_dev = timed_steps(graphed, S)
     barrier()
     t_dev_noflush = timed_steps(graphed, S, do_flush=False)
@@ -627,7 +633,7 @@ def main():
         line = {
             "metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": S,
             "warmup": W, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32", "data": "synthetic", "ms_per_step_median_rank0": float(np.median(t_dev)), "ms_per_step_max_rank0": float(np.max(t_dev)),
             "value_no_l2_flush": total_frames / (ms_dev_noflush * 1e-3), "ms_per_step_no_l2_flush": ms_dev_noflush,
             "value_static_rig": total_frames / (ms_static * 1e-3), "ms_per_step_static_rig": ms_static,
             "value_eager": total_frames / (ms_eager * 1e-3), "ms_per_step_eager": ms_eager,
