@@ -222,13 +222,14 @@ def run_train(args, cfg: LiftConfig, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize()
 
     def timed(fn):
-        ts = []
+        pairs = []
         for _ in range(S):
             flush.fill_(1.0)
             a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); e.record(); e.synchronize()
-            ts.append(a.elapsed_time(e))
-        return float(np.mean(ts))
+            a.record(); fn(); e.record()
+            pairs.append((a, e))
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(e) for a, e in pairs]))
 
     def step_dev():
         trainer.step(batch)
@@ -387,8 +388,10 @@ def main():
         torch.cuda.synchronize()
 
     def timed_steps(step_fn, n_steps, do_flush=True):
-        """Per-step CUDA events on the current stream; L2 flushed (256 MiB write) before each step, outside the events."""
-        times = []
+        """Per-step CUDA events on the current stream; L2 flushed (256 MiB write) before each step, outside the events.  All steps
+        are enqueued before the host waits, so a step's interval is device time: a descheduled host thread between the start event
+        and the launch would otherwise show up as a multi-millisecond "step" (seen at N = 8, profiles/r02_notes.md)."""
+        pairs = []
         for _ in range(n_steps):
             if do_flush:
                 flush.fill_(1.0)
@@ -396,9 +399,9 @@ def main():
             a.record()
             step_fn()
             b.record()
-            b.synchronize()
-            times.append(a.elapsed_time(b))
-        return times
+            pairs.append((a, b))
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in pairs]
 
     # ---- value: device-resident inputs through the public API ----------------------------------------------------------
     # LiftSplat.capture() records the forward lift (TMA descriptors + the tile-kernel / layout-pass chains of every frame group, forked

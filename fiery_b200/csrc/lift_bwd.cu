@@ -346,15 +346,22 @@ lift_backward_kernel(const __grid_constant__ HeadMapsCols head_maps, const __gri
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// grad_bev (B', C, X*Y) -> channel-last workspace (B', X*Y, C)
+// grad_bev (B', C, X*Y) -> channel-last workspace (B', X*Y, C).  The backward only gathers the rows of pillars that receive a
+// point (~1/3 of the grid, clustered around the rig): with the plan's touched map a block of 64 pillars that has none is skipped
+// entirely -- neither read nor written.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TR_PILLARS = 64;
 __global__ void __launch_bounds__(256)
-nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, long long pillars, int blocks_per_frame) {
+nchw_to_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, const unsigned char* __restrict__ touched, int C,
+                    long long pillars, int blocks_per_frame) {
     __shared__ float tile[TR_PILLARS][65];
     const int frame = blockIdx.x / blocks_per_frame;
     const long long p0 = static_cast<long long>(blockIdx.x % blocks_per_frame) * TR_PILLARS;
     const int n_here = static_cast<int>(min(static_cast<long long>(TR_PILLARS), pillars - p0));
+    if (touched) {
+        const int mine = (threadIdx.x < n_here) ? touched[static_cast<size_t>(frame) * pillars + p0 + threadIdx.x] : 0;
+        if (!__syncthreads_or(mine)) return;
+    }
     const float* s = src + static_cast<size_t>(frame) * C * pillars + p0;
     for (int i = threadIdx.x; i < C * TR_PILLARS; i += 256) {
         const int c = i / TR_PILLARS, pl = i % TR_PILLARS;
@@ -391,7 +398,8 @@ int launch_lift_backward(const LiftParams& P, const void* head, int head_dtype, 
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     if (P.bev_layout == FIERY_BEV_NCHW) {
         const int bpf = static_cast<int>((P.pillars + TR_PILLARS - 1) / TR_PILLARS);
-        nchw_to_nhwc_kernel<<<static_cast<unsigned>(bpf) * P.n_frames, 256, 0, stream>>>(P.grad_bev, workspace, P.C, P.pillars, bpf);
+        const unsigned char* marks = plan ? plan_view(plan, P.n_frames, P.n_cameras, P.n_wtiles, P.pillars, 0).touched : nullptr;
+        nchw_to_nhwc_kernel<<<static_cast<unsigned>(bpf) * P.n_frames, 256, 0, stream>>>(P.grad_bev, workspace, marks, P.C, P.pillars, bpf);
         FIERY_CUDA_CHECK(cudaGetLastError());
         Q.grad_bev = workspace;
         ws += (lift_backward_relayout_bytes(P) + 127) & ~static_cast<size_t>(127);

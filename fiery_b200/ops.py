@@ -47,10 +47,12 @@ def lift_splat(head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.T
     m = _module(handle)
     native = head.dtype == torch.float32 or (head.dtype == torch.float16 and L.NATIVE_FP16_FORWARD)
     head_in = head if native else head.float()
+    made = None
     if plan is None and make_plan and intrinsics.shape[0]:
-        plan = m.plan(intrinsics.to(head.device), extrinsics)
-    out = m._launch_forward(head_in, intrinsics, extrinsics, plan=plan)
-    return out, (plan if plan is not None else torch.empty(0, dtype=torch.uint8, device=head.device))
+        made = m.plan(intrinsics.to(head.device), extrinsics)
+    out = m._launch_forward(head_in, intrinsics, extrinsics, plan=plan if plan is not None else made)
+    # the second output is the plan MADE here (an operator output may not alias an input: a plan that was passed in is not returned)
+    return out, (made if made is not None else torch.empty(0, dtype=torch.uint8, device=head.device))
 
 
 @lift_splat.register_fake
