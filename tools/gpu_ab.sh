@@ -3,6 +3,8 @@
 # kernel, then number of frame-group chains x minimum tiles per group (AB_COMBOS = "chains:min_tiles ..."), forward (eager and
 # graph) and backward, then the lift parity tests on the requested combinations (AB_TEST, same format)
 mkdir -p gpurun_out
+# the experiment build sits next to the in-tree library: FIERY_NVCC_EXTRA=-DFIERY_COLS_AB python -m fiery_b200.build --out fiery_b200/libfiery_b200_ab.so
+export FIERY_B200_LIB=${FIERY_B200_LIB:-$PWD/fiery_b200/libfiery_b200_ab.so}
 for w in cfg2_static_lss_b8 cfg3_baseline cfg4_pon; do
   echo "== $w"; timeout 600 python tools/ab_forward.py $w 2>&1 | grep -E "^tile|^chains|Error|error" | cut -c1-330
 done

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Small ncu target: runs only the launches to be captured, through the C ABI.
     python tools/ncu_target.py <workload> tile    # the column tile kernel alone (channel-last target), whole batch, 4 launches
+    python tools/ncu_target.py <workload> tile_planned   # the same with a caller-owned geometry plan (planned variant of the kernel)
     python tools/ncu_target.py <workload> step    # the NCHW step (tile kernels + layout passes of every frame group), 4 calls
     python tools/ncu_target.py <workload> bwd     # NCHW backward (re-layout + backward tile kernel), 3 calls
     python tools/ncu_target.py <workload> conv    # the tcgen05 first BEV convolution on a channel-last BEV of the workload's size, 4 calls
@@ -35,11 +36,12 @@ elif mode == "bwd":
     for _ in range(3):
         lift._launch_backward(head, K_d, E_d, g)
 else:
-    layout = _lib.BEV_NHWC if mode == "tile" else _lib.BEV_NCHW
+    layout = _lib.BEV_NHWC if mode.startswith("tile") else _lib.BEV_NCHW
+    plan = lift.plan(K_d, E_d) if mode == "tile_planned" else None
     desc = lift._desc(c, cfg.frames, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, layout)
-    out = torch.zeros((cfg.frames, X, Y, cfg.out_channels) if mode == "tile" else (cfg.frames, cfg.out_channels, X, Y), device=dev)
+    out = torch.zeros((cfg.frames, X, Y, cfg.out_channels) if mode.startswith("tile") else (cfg.frames, cfg.out_channels, X, Y), device=dev)
     scratch = torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(desc)) // 4), dtype=torch.float32, device=dev)
     for _ in range(4):
         _lib.check(lib.fiery_lift_forward(desc, head.data_ptr(), K_d.data_ptr(), E_d.data_ptr(), c["u"].data_ptr(), c["v"].data_ptr(),
-                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), None, _stream_ptr(dev)), "fwd")
+                                          c["d"].data_ptr(), out.data_ptr(), scratch.data_ptr(), plan.data_ptr() if plan is not None else None, _stream_ptr(dev)), "fwd")
 torch.cuda.synchronize()
