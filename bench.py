@@ -333,7 +333,8 @@ def main():
                          "forward tile kernel reads the half-precision tensor itself; all arithmetic stays fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the VoxelsSumming / warp / reference-ops-on-GPU side measurements")
-    ap.add_argument("--e2e-chunk", type=int, default=2, help="frames per upload/lift/download pipeline stage in the e2e run")
+    ap.add_argument("--e2e-chunk", default="1,2", help="frames per upload/lift/download pipeline stage in the e2e run: one number, or the "
+                                                      "sizes of the first stages (the last repeats)")
     ap.add_argument("--cpu-frames", type=int, default=3)
     ap.add_argument("--cpu-reps", type=int, default=5)
     args = ap.parse_args()
@@ -449,11 +450,40 @@ def main():
     def step_bwd_only(g):
         return lift._launch_backward(head_f32, K_d, E_d, g, plan=plan_d)
 
+    # the lift's training path as device time: plan -> forward (planned) -> backward, through the C ABI with static buffers, captured in
+    # a CUDA graph (the eager autograd step above is host-bound: ~30 launches and 4 large allocations from Python per step)
+    c0 = lift._constants(dev)
+    d_tr = lift._desc(c0, frames, cfg.n_cameras, torch.float32, _lib.CALIB_RAW, _lib.BEV_NCHW)
+    tr_plan = torch.empty(int(lib.fiery_lift_plan_bytes(d_tr)), dtype=torch.uint8, device=dev)
+    tr_scratch = torch.zeros(max(1, int(lib.fiery_lift_scratch_bytes(d_tr)) // 4), dtype=torch.float32, device=dev)
+    tr_ws = torch.empty(max(1, int(lib.fiery_lift_workspace_bytes(d_tr)) // 4), dtype=torch.float32, device=dev)
+    tr_out = torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32, device=dev)
+    tr_grad = torch.empty_like(head_f32)
+
+    def train_path(sp):
+        args6 = (K_d.data_ptr(), E_d.data_ptr(), c0["u"].data_ptr(), c0["v"].data_ptr(), c0["d"].data_ptr())
+        _lib.check(lib.fiery_lift_plan(d_tr, *args6, tr_plan.data_ptr(), sp), "plan")
+        _lib.check(lib.fiery_lift_forward(d_tr, head_f32.data_ptr(), *args6, tr_out.data_ptr(), tr_scratch.data_ptr(), tr_plan.data_ptr(), sp), "fwd")
+        _lib.check(lib.fiery_lift_backward(d_tr, head_f32.data_ptr(), *args6, gout_d.data_ptr(), tr_grad.data_ptr(), tr_ws.data_ptr(),
+                                           tr_plan.data_ptr(), sp), "bwd")
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            train_path(side.cuda_stream)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g_train = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_train):
+        train_path(torch.cuda.current_stream(dev).cuda_stream)
+
     for _ in range(3):
         step_fwd_bwd()
         step_bwd_only(gout_d)
         step_bwd_only(gout_cl)
+        g_train.replay()
     barrier()
+    t_fb_graph = timed_steps(g_train.replay, S)
     t_fb = timed_steps(step_fwd_bwd, S)
     t_bwd = timed_steps(lambda: step_bwd_only(gout_d), S)
     t_bwd_cl = timed_steps(lambda: step_bwd_only(gout_cl), S)
@@ -464,9 +494,11 @@ def main():
     K_h, E_h = torch.from_numpy(K).pin_memory(), torch.from_numpy(E).pin_memory()
     out_h = torch.empty((frames, cfg.out_channels, X, Y), dtype=torch.float32).pin_memory()
 
+    e2e_chunks = [int(x) for x in str(args.e2e_chunk).split(",")]
+
     def step_e2e():
         # public host-buffer entry point: chunked upload / lift / download on three streams; returns after the BEV is on the host
-        lift.lift_from_host(head_h, K_h, E_h, out=out_h, device=dev, chunk_frames=args.e2e_chunk)
+        lift.lift_from_host(head_h, K_h, E_h, out=out_h, device=dev, chunk_frames=e2e_chunks)
 
     for _ in range(3):
         step_e2e()
@@ -601,6 +633,7 @@ def main():
     ms_static = reduce_max(float(np.mean(t_static)))
     ms_eager = reduce_max(float(np.mean(t_eager)))
     ms_fb = reduce_max(float(np.mean(t_fb)))
+    ms_fb_graph = reduce_max(float(np.mean(t_fb_graph)))
     ms_bwd = reduce_max(float(np.mean(t_bwd)))
     ms_bwd_cl = reduce_max(float(np.mean(t_bwd_cl)))
     ms_e2e = reduce_max(float(np.mean(t_e2e)))
@@ -640,8 +673,12 @@ def main():
             "value_no_l2_flush": total_frames / (ms_dev_noflush * 1e-3), "ms_per_step_no_l2_flush": ms_dev_noflush,
             "value_static_rig": total_frames / (ms_static * 1e-3), "ms_per_step_static_rig": ms_static,
             "value_eager": total_frames / (ms_eager * 1e-3), "ms_per_step_eager": ms_eager,
-            "fwd_bwd": {"value": total_frames / (ms_fb * 1e-3), "unit": "frames/s", "ms_per_step": ms_fb,
-                        "what": "LiftSplat.forward + autograd backward to the head tensor (eager; the plan is computed once and shared)"},
+            "fwd_bwd": {"value": total_frames / (ms_fb_graph * 1e-3), "unit": "frames/s", "ms_per_step": ms_fb_graph,
+                        "frac_of_hbm_peak": (cfg.fwd_bytes_per_frame(4) + cfg.bwd_bytes_per_frame(4)) * frames / (ms_fb_graph * 1e-3) / 1e9 / load_peaks()[0],
+                        "ms_per_step_eager_autograd": ms_fb,
+                        "what": "the lift's training path: geometry plan + forward (planned) + backward to the head tensor, NCHW BEV and "
+                                "gradient, C ABI with static buffers, CUDA-graph replay (device time); ms_per_step_eager_autograd = "
+                                "LiftSplat.forward + autograd backward from Python (host-bound)"},
             "config": config_dict(cfg, args, world),          # identical in both arms
             "details": {"parallelism": f"frames sharded over {world} GPU(s), no data-path collective",
                         "l2": "flushed before every timed step (256 MiB write); step time = CUDA events around the step",

@@ -285,12 +285,14 @@ class LiftSplat(nn.Module):
 
     def lift_from_host(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
                        out: Optional[torch.Tensor] = None, device: Optional[torch.device] = None,
-                       chunk_frames: int = 3) -> torch.Tensor:
+                       chunk_frames=3) -> torch.Tensor:
         """Host-buffer entry point: ``head`` (B'*n, D+C, h, w), ``intrinsics`` (B', n, 3, 3), ``extrinsics`` (B', n, 4, 4) in
         (pinned) host memory -> BEV (B', C, X, Y) in pinned host memory.  Frames are independent, so the batch is cut into
         chunks of ``chunk_frames`` and the three stages -- host->device copy, lift, device->host copy -- run on three
         streams, overlapping the upload of chunk i+1 and the download of chunk i-1 with the lift of chunk i (PCIe is
-        full duplex).  Synchronises before returning.  Inference only."""
+        full duplex).  ``chunk_frames`` may be a sequence: the sizes of the first chunks (the last entry repeats) -- a small first
+        chunk starts the download earlier, and the download of 82 MB per 8 frames is what bounds the call.  Synchronises before
+        returning.  Inference only."""
         dev = device if device is not None else next(self.parameters()).device
         if dev.type != "cuda":
             raise _lib.FieryError("lift_from_host needs the module on a CUDA device: fiery_b200 has no CPU path")
@@ -306,9 +308,14 @@ class LiftSplat(nn.Module):
             s.wait_stream(cur)
         up, run, down = st
         prev_done = None
+        sizes = [max(1, int(c)) for c in (chunk_frames if isinstance(chunk_frames, (list, tuple)) else [chunk_frames])]
+        bounds, f0 = [], 0
+        while f0 < B:
+            n_here = sizes[min(len(bounds), len(sizes) - 1)]
+            bounds.append((f0, min(B, f0 + n_here)))
+            f0 += n_here
         with torch.no_grad():
-            for f0 in range(0, B, max(1, chunk_frames)):
-                f1 = min(B, f0 + max(1, chunk_frames))
+            for f0, f1 in bounds:
                 with torch.cuda.stream(up):
                     h = head[f0 * n:f1 * n].to(dev, non_blocking=True)
                     k = intrinsics[f0:f1].to(dev, non_blocking=True)
