@@ -59,6 +59,7 @@ SIGNATURES = {
     "fiery_voxels_summing_forward": (c_int32, [c_int64, c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                                c_void_p, c_void_p, c_void_p]),
     "fiery_voxels_summing_backward": (c_int32, [c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "fiery_depth_layer_forward": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "fiery_bev_conv_pack_weights": (c_int32, [c_void_p, c_void_p, c_void_p]),
     "fiery_bev_first_conv_forward": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "fiery_warp_theta": (c_int32, [c_int32, c_int32, c_int32, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p]),

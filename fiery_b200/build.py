@@ -18,7 +18,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libfiery_b200.so")
 STAMP_PATH = os.path.join(PKG_DIR, "csrc", ".build_stamp")
-SOURCES = ["c_api.cu", "lift_plan.cu", "lift_fwd.cu", "lift_fwd_cols.cu", "lift_bwd.cu", "bev_conv.cu", "voxels_summing.cu", "warp.cu"]
+SOURCES = ["c_api.cu", "lift_plan.cu", "lift_fwd.cu", "lift_fwd_cols.cu", "lift_bwd.cu", "bev_conv.cu", "depth_layer.cu", "voxels_summing.cu", "warp.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo", "--use_fast_math=false",

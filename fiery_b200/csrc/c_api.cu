@@ -154,6 +154,8 @@ int launch_warp_theta(int n_seq, int T, int cumulative, const float* flow, float
 int launch_pack_conv_weights(const float* w_oihw, float* packed, cudaStream_t stream);
 int launch_bev_conv(int n_frames, int H, int W, const float* x_nhwc, const float* w_packed, const float* scale, const float* shift,
                     int relu, float* y_nhwc, cudaStream_t stream);
+int launch_depth_layer(int n_images, int pixels, int n_out, const void* feat, int dtype, const void* weight_padded, const float* bias,
+                       float* head, cudaStream_t stream);
 int vs_plan(int64_t n_rows, const int64_t* ranks, int32_t* seg, int64_t* host_n, cudaStream_t);
 int vs_forward(int64_t n_rows, int channels, int64_t feat_stride, const float* feats, const int64_t* coords,
                const int32_t* seg, int64_t n_seg, float* sums, int64_t* coords_out, cudaStream_t);
@@ -378,6 +380,12 @@ FIERY_API int fiery_bev_first_conv_forward(int32_t n_frames, int32_t height, int
                                            const float* scale, const float* shift, int32_t relu, float* y_nhwc, void* stream) {
     FIERY_REQUIRE(n_frames == 0 || (x_nhwc && packed_weight && y_nhwc), "bev conv: NULL pointer");
     return launch_bev_conv(n_frames, height, width, x_nhwc, packed_weight, scale, shift, relu ? 1 : 0, y_nhwc, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_depth_layer_forward(int32_t n_images, int32_t pixels, int32_t n_out, const void* feat, int32_t dtype,
+                                        const void* weight_padded, const float* bias, float* head_out, void* stream) {
+    FIERY_REQUIRE(n_images == 0 || (feat && weight_padded && head_out), "depth layer: NULL pointer");
+    return launch_depth_layer(n_images, pixels, n_out, feat, dtype, weight_padded, bias, head_out, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

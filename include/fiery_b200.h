@@ -16,6 +16,8 @@
  *       exposes the integer voxel coordinates the reference computes at fiery.py:236-256 (for parity checks)
  *   fiery_compose_calibration
  *       exposes combined = R @ inverse(K), translation  (fiery.py:196,203)
+ *   fiery_depth_layer_forward
+ *       replaces Encoder.depth_layer (the head tensor's producer)  fiery/models/encoder.py:36,96   [SURVEY.md section 8f, next-3]
  *   fiery_bev_first_conv_forward
  *       replaces Decoder.first_conv (+ bn1 + relu in eval mode)  fiery/models/decoder.py:11,59-61   [SURVEY.md section 8f, next-2]
  *   fiery_warp_features_forward / _backward, fiery_warp_theta
@@ -221,6 +223,16 @@ FIERY_API int fiery_warp_theta(int32_t n_sequences, int32_t T, int32_t cumulativ
 FIERY_API int fiery_bev_conv_pack_weights(const float* weight_oihw, float* packed_out, void* stream);
 FIERY_API int fiery_bev_first_conv_forward(int32_t n_frames, int32_t height, int32_t width, const float* x_nhwc, const float* packed_weight,
                                            const float* scale, const float* shift, int32_t relu, float* y_nhwc, void* stream);
+
+/*
+ * Encoder.depth_layer on the tensor cores -- the 1x1 convolution 128 -> D + C that produces the head tensor
+ * (fiery/models/encoder.py:36,96): head_out (n_images, n_out, pixels) fp32 = weight @ feat + bias, computed by tcgen05 (fp16 / bf16
+ * operands under AMP, TF32 for fp32 features; fp32 accumulation).  feat: (n_images, 128, pixels) with pixels = h*w, dtype 0 fp32 /
+ * 1 fp16 / 2 bf16; weight_padded: (128, 128) row-major in the SAME dtype, rows >= n_out zero; bias: n_out floats or NULL.  Writing the
+ * fp32 head directly removes the widening pass an AMP step otherwise needs in front of the lift.  [SURVEY.md section 8f, next-3]
+ */
+FIERY_API int fiery_depth_layer_forward(int32_t n_images, int32_t pixels, int32_t n_out, const void* feat, int32_t dtype,
+                                        const void* weight_padded, const float* bias, float* head_out, void* stream);
 
 #ifdef __cplusplus
 }
