@@ -268,6 +268,31 @@ def run_train(args, cfg: LiftConfig, rank: int, local_rank: int, world: int):
         lift_only()
     ms_lift = timed(lift_only)
 
+    depth_extra = None
+    if rank == 0 and not args.no_extras:
+        from fiery_b200.depth_layer import depth_layer_forward, pack_weight as pack_depth_weight
+        n_out = cfg.head_channels
+        fh, fw = cfg.feat_hw
+        feat16 = torch.randn(frames * cfg.n_cameras, 128, fh, fw, device=dev).half()          # the backbone's output under AMP
+        wd = torch.randn(n_out, 128, 1, 1, device=dev) * 0.05
+        bd = torch.randn(n_out, device=dev)
+        wdp, wd16, bd16 = pack_depth_weight(wd, torch.float16), wd.half(), bd.half()
+        with torch.no_grad():
+            for _ in range(3):
+                depth_layer_forward(feat16, wd, bd, wdp)
+                torch.nn.functional.conv2d(feat16, wd16, bd16).float()
+            d_ms = float(np.mean(timed_steps(lambda: depth_layer_forward(feat16, wd, bd, wdp), S)))
+            dl_ms = float(np.mean(timed_steps(lambda: torch.nn.functional.conv2d(feat16, wd16, bd16), S)))
+            dlw_ms = float(np.mean(timed_steps(lambda: torch.nn.functional.conv2d(feat16, wd16, bd16).float(), S)))
+        d_bytes = feat16.numel() * 2 + feat16.shape[0] * n_out * fh * fw * 4 + 128 * 128 * 2
+        depth_extra = {"frames": frames, "ms_per_call": d_ms, "bytes": d_bytes, "achieved_gbs": d_bytes / (d_ms * 1e-3) / 1e9,
+                       "library_cudnn_fp16_ms": dl_ms, "library_cudnn_fp16_plus_widening_ms": dlw_ms,
+                       "what": "fiery_b200.depth_layer.depth_layer_forward (Encoder.depth_layer, encoder.py:36,96: persistent tcgen05 "
+                               "kind::f16 GEMM, fp16 NCHW features in, fp32 NCHW head tensor out, TMA both ways); bytes = features "
+                               "read once + head written once + weights; library lines: torch conv2d (cuDNN, fp16 out) alone and "
+                               "followed by the .float() an AMP step needs before the fp32 lift; L2 flushed before every call"}
+        del feat16
+
     def reduce_max(x):
         if not distributed:
             return x
@@ -621,6 +646,31 @@ def main():
                               "channel-last (B', 200, 200, 64) fp32 BEV; peak = measured cuBLAS bf16 burst / 2 (TF32 runs at half the "
                               "bf16 rate); library line: torch conv2d, cuDNN with allow_tf32, same tensors; L2 flushed before every call"}
 
+    depth_extra = None
+    if rank == 0 and not args.no_extras:
+        from fiery_b200.depth_layer import depth_layer_forward, pack_weight as pack_depth_weight
+        n_out = cfg.head_channels
+        fh, fw = cfg.feat_hw
+        feat16 = torch.randn(frames * cfg.n_cameras, 128, fh, fw, device=dev).half()          # the backbone's output under AMP
+        wd = torch.randn(n_out, 128, 1, 1, device=dev) * 0.05
+        bd = torch.randn(n_out, device=dev)
+        wdp, wd16, bd16 = pack_depth_weight(wd, torch.float16), wd.half(), bd.half()
+        with torch.no_grad():
+            for _ in range(3):
+                depth_layer_forward(feat16, wd, bd, wdp)
+                torch.nn.functional.conv2d(feat16, wd16, bd16).float()
+            d_ms = float(np.mean(timed_steps(lambda: depth_layer_forward(feat16, wd, bd, wdp), S)))
+            dl_ms = float(np.mean(timed_steps(lambda: torch.nn.functional.conv2d(feat16, wd16, bd16), S)))
+            dlw_ms = float(np.mean(timed_steps(lambda: torch.nn.functional.conv2d(feat16, wd16, bd16).float(), S)))
+        d_bytes = feat16.numel() * 2 + feat16.shape[0] * n_out * fh * fw * 4 + 128 * 128 * 2
+        depth_extra = {"frames": frames, "ms_per_call": d_ms, "bytes": d_bytes, "achieved_gbs": d_bytes / (d_ms * 1e-3) / 1e9,
+                       "library_cudnn_fp16_ms": dl_ms, "library_cudnn_fp16_plus_widening_ms": dlw_ms,
+                       "what": "fiery_b200.depth_layer.depth_layer_forward (Encoder.depth_layer, encoder.py:36,96: persistent tcgen05 "
+                               "kind::f16 GEMM, fp16 NCHW features in, fp32 NCHW head tensor out, TMA both ways); bytes = features "
+                               "read once + head written once + weights; library lines: torch conv2d (cuDNN, fp16 out) alone and "
+                               "followed by the .float() an AMP step needs before the fp32 lift; L2 flushed before every call"}
+        del feat16
+
     def reduce_max(x):
         if not distributed:
             return x
@@ -717,6 +767,9 @@ def main():
             line["voxels_summing_dropin"] = vs_extra
         if conv_extra is not None:
             line["next_row_first_bev_conv"] = conv_extra
+        if depth_extra is not None:
+            depth_extra["frac_of_hbm_peak"] = depth_extra["achieved_gbs"] / peak
+            line["next_row_depth_layer"] = depth_extra
         if warp_extra is not None:
             warp_extra["frac_of_hbm_peak"] = warp_extra["achieved_gbs"] / peak
             line["next_row_cumulative_warp"] = warp_extra

@@ -12,8 +12,8 @@
 //          TMA boxes of (128 bytes of pixels) x (128 channels), 128-byte swizzle)
 // Because the accumulator's rows are output CHANNELS and its columns consecutive PIXELS, the epilogue thread that owns row o writes
 // 512 contiguous bytes of plane o of the NCHW head tensor -- no transposition anywhere.
-// Warp roles: warp 0 TMA producer, warp 1 TMEM allocation + MMA issue (8 x kind::f16 K16 or 16 x kind::tf32 K8), warps 2-5 epilogue
-// (tcgen05.ld 32 columns at a time, + bias, 16-byte stores).
+// Warp roles: warp 0 TMA producer, warp 1 TMEM allocation + MMA issue (8 x kind::f16 K16 or 16 x kind::tf32 K8), warps 2-9 epilogue
+// (two warps per TMEM lane quarter; tcgen05.ld 2 x 32 columns, + bias, swizzled staging boxes, TMA stores).
 #include "lift_plan.cuh"
 
 namespace fiery {
@@ -21,7 +21,8 @@ namespace fiery {
 constexpr int DL_K = 128;                 // input channels (upsampling_out_channels, encoder.py:33)
 constexpr int DL_M = 128;                 // padded output channels
 constexpr int DL_N = 128;                 // pixels per tile
-constexpr int DL_THREADS = 192;
+constexpr int DL_EPI_WARPS = 8;              // two per TMEM lane quarter, each takes half of the tile's pixel columns
+constexpr int DL_THREADS = 64 + 32 * DL_EPI_WARPS;
 constexpr int DL_TMEM_COLS = 256;             // two accumulators
 
 struct DepthLayerMaps {
@@ -30,7 +31,6 @@ struct DepthLayerMaps {
     CUtensorMap out;      // (pixels, n_out, images) fp32, box (32 pixels, 32 channels, 1), swizzle 128B
     int pixels;
 };
-__device__ __forceinline__ int maps_pixels(const DepthLayerMaps& m) { return m.pixels; }
 
 __device__ __forceinline__ void tma_load_2d_sw(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -73,7 +73,8 @@ struct DlShape {
     static constexpr int A_BYTES = ATOMS * A_ATOM, B_BYTES = NBLK * B_BLK;
     static constexpr int STAGES = ES == 2 ? 3 : 2;            // feature tiles in flight (32 KB / 64 KB each)
     static constexpr int OUT_BUF = 32 * 128;                  // one epilogue warp's staging box: 32 channels x 32 pixels fp32
-    static constexpr int OUT_BYTES = 4 * 2 * OUT_BUF;         // 4 warps, double-buffered
+    static constexpr int OUT_BUFS = ES == 2 ? 2 : 1;          // staging boxes per warp (the fp32 variant's feature ring leaves room for one)
+    static constexpr int OUT_BYTES = DL_EPI_WARPS * OUT_BUFS * OUT_BUF;
     static constexpr int SMEM = A_BYTES + STAGES * B_BYTES + OUT_BYTES + 1024 + 256;
 };
 
@@ -84,8 +85,13 @@ struct DlShape {
 template <int ES>
 __global__ void __launch_bounds__(DL_THREADS, 1)
 depth_layer_kernel(const __grid_constant__ DepthLayerMaps maps, const float* __restrict__ bias, int n_out, int tiles_per_image,
-                   int n_tiles, uint32_t idesc) {
+                   int n_tiles, uint32_t idesc, int skip_arg) {
     using S = DlShape<ES>;
+#ifdef FIERY_COLS_AB
+    const int skip = skip_arg;                         // experiment builds: leave out stores (1) / MMAs (2) / feature loads (4)
+#else
+    constexpr int skip = 0;
+#endif
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     unsigned char* s_a = smem;
@@ -111,7 +117,7 @@ depth_layer_kernel(const __grid_constant__ DepthLayerMaps maps, const float* __r
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(acc_full + i, 1);
-            mbar_init(acc_empty + i, 4);                // one arrival per epilogue warp
+            mbar_init(acc_empty + i, DL_EPI_WARPS);     // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -135,6 +141,7 @@ depth_layer_kernel(const __grid_constant__ DepthLayerMaps maps, const float* __r
                 if (use > 0) mbar_wait(b_empty + st, (use - 1) & 1);
                 const int img = t / tiles_per_image, p0 = (t % tiles_per_image) * DL_N;
                 unsigned char* dst = s_b + st * S::B_BYTES;
+                if (skip & 4) { mbar_arrive(b_full + st); continue; }
                 mbar_arrive_expect_tx(b_full + st, S::B_BYTES);
 #pragma unroll
                 for (int b = 0; b < S::NBLK; ++b) tma_load_3d(dst + b * S::B_BLK, &maps.feat, b_full + st, p0 + b * S::EPR, 0, img);   // pixels past the image: zeros
@@ -154,7 +161,7 @@ depth_layer_kernel(const __grid_constant__ DepthLayerMaps maps, const float* __r
                 const uint32_t b_addr = smem_addr(s_b + st * S::B_BYTES);
                 const uint32_t d_addr = tmem_base + acc * DL_N;
 #pragma unroll
-                for (int k = 0; k < DL_K / S::UMMA_K; ++k) {
+                for (int k = 0; k < ((skip & 2) ? 0 : DL_K / S::UMMA_K); ++k) {
                     const int k0 = k * S::UMMA_K;
                     // A: atom k0 / EPR, 32 bytes per K step inside the atom.  B: k0 rows of 128 bytes down the block; blocks along N 16 KB apart.
                     const uint64_t da = dl_desc(a_addr + (k0 / S::EPR) * S::A_ATOM + (k0 % S::EPR) * ES, 16, 1024);
@@ -172,57 +179,63 @@ depth_layer_kernel(const __grid_constant__ DepthLayerMaps maps, const float* __r
         }
     } else {                                           // ===== epilogue: accumulator row = output channel, columns = pixels =====
         const int q = warp & 3;                        // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;              // which 64 pixel columns of the tile
         const int o = q * 32 + lane;
         const float bo = (o < n_out && bias) ? __ldg(bias + o) : 0.f;
-        unsigned char* my_out = s_out + q * 2 * S::OUT_BUF;
+        unsigned char* my_out = s_out + (warp - 2) * S::OUT_BUFS * S::OUT_BUF;
         const bool rows_live = q * 32 < n_out;         // channels past n_out: the store's box lies outside the tensor
+        const int pixels = maps.pixels;
         int it = 0, nbox = 0;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1, acc_use = it >> 1;
-            const int img = t / tiles_per_image, p0 = (t % tiles_per_image) * DL_N;
+            const int img = t / tiles_per_image, p0 = (t % tiles_per_image) * DL_N + half * 64;
             mbar_wait(acc_full + acc, acc_use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * DL_N;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * DL_N + half * 64;
+            uint32_t v[2][32];
 #pragma unroll
-            for (int c = 0; c < DL_N; c += 32) {
-                uint32_t v[32];
+            for (int c = 0; c < 2; ++c)
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                      "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-                      "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-                      "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr + c)
+                    : "=r"(v[c][0]), "=r"(v[c][1]), "=r"(v[c][2]), "=r"(v[c][3]), "=r"(v[c][4]), "=r"(v[c][5]), "=r"(v[c][6]), "=r"(v[c][7]),
+                      "=r"(v[c][8]), "=r"(v[c][9]), "=r"(v[c][10]), "=r"(v[c][11]), "=r"(v[c][12]), "=r"(v[c][13]), "=r"(v[c][14]),
+                      "=r"(v[c][15]), "=r"(v[c][16]), "=r"(v[c][17]), "=r"(v[c][18]), "=r"(v[c][19]), "=r"(v[c][20]), "=r"(v[c][21]),
+                      "=r"(v[c][22]), "=r"(v[c][23]), "=r"(v[c][24]), "=r"(v[c][25]), "=r"(v[c][26]), "=r"(v[c][27]), "=r"(v[c][28]),
+                      "=r"(v[c][29]), "=r"(v[c][30]), "=r"(v[c][31])
+                    : "r"(taddr + c * 32)
                     : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + 32 == DL_N) {                  // the accumulator is in registers: hand it back to the MMA warp
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty + acc);
-                }
-                if (rows_live && p0 + c < maps_pixels(maps)) {
-                    unsigned char* buf = my_out + (nbox & 1) * S::OUT_BUF;
-                    if (nbox >= 2) {                   // the store that last read this buffer must have drained it
-                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // the accumulator is in registers: hand it back
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + acc);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if (rows_live && p0 + c * 32 < pixels && !(skip & 1)) {
+                    unsigned char* buf = my_out + (nbox % S::OUT_BUFS) * S::OUT_BUF;
+                    if (nbox >= S::OUT_BUFS) {         // the store that last read this buffer must have drained it
+                        if (lane == 0) {
+                            if (S::OUT_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                        }
                         __syncwarp();
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j)        // row = lane (128 B), 16-byte chunk j at j ^ (row % 8): the 128-byte swizzle of the store's map
                         *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                            make_float4(__uint_as_float(v[4 * j]) + bo, __uint_as_float(v[4 * j + 1]) + bo, __uint_as_float(v[4 * j + 2]) + bo,
-                                        __uint_as_float(v[4 * j + 3]) + bo);
+                            make_float4(__uint_as_float(v[c][4 * j]) + bo, __uint_as_float(v[c][4 * j + 1]) + bo,
+                                        __uint_as_float(v[c][4 * j + 2]) + bo, __uint_as_float(v[c][4 * j + 3]) + bo);
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_3d(&maps.out, buf, p0 + c, q * 32, img);     // clipped at the image's last pixel and at channel n_out
+                        tma_store_3d(&maps.out, buf, p0 + c * 32, q * 32, img);     // clipped at the image's last pixel and at channel n_out
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++nbox;
                 }
             }
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the stores read shared memory until they complete
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the stores' reads
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -314,8 +327,12 @@ int launch_depth_layer(int n_images, int pixels, int n_out, const void* feat, in
     const int sms = n_sm[dev & 63] > 0 ? n_sm[dev & 63] : 148;
     const int waves = (n_tiles + sms - 1) / sms;                       // one persistent CTA per SM, the tiles spread evenly over them
     const unsigned grid = static_cast<unsigned>((n_tiles + waves - 1) / waves);
-    if (es == 2) depth_layer_kernel<2><<<grid, DL_THREADS, DlShape<2>::SMEM, stream>>>(maps, bias, n_out, tiles_per_image, n_tiles, idesc);
-    else depth_layer_kernel<4><<<grid, DL_THREADS, DlShape<4>::SMEM, stream>>>(maps, bias, n_out, tiles_per_image, n_tiles, idesc);
+    int skip = 0;
+#ifdef FIERY_COLS_AB
+    if (const char* e = getenv("FIERY_DL_SKIP")) skip = atoi(e);      // experiment builds only: 1 no stores, 2 no MMAs, 4 no feature loads
+#endif
+    if (es == 2) depth_layer_kernel<2><<<grid, DL_THREADS, DlShape<2>::SMEM, stream>>>(maps, bias, n_out, tiles_per_image, n_tiles, idesc, skip);
+    else depth_layer_kernel<4><<<grid, DL_THREADS, DlShape<4>::SMEM, stream>>>(maps, bias, n_out, tiles_per_image, n_tiles, idesc, skip);
     FIERY_CUDA_CHECK(cudaGetLastError());
     return FIERY_OK;
 }

@@ -61,13 +61,20 @@ class _DepthLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):                                  # g (N, n_out, h, w) fp32: the lift's grad_head
+        """Library GEMMs in the features' dtype -- what the reference's convolution backward runs in under autocast (half operands,
+        fp32 accumulation, loss-scaled gradients); fp32 features keep fp32 GEMMs."""
         feat, weight = ctx.saved_tensors
         n_out = weight.shape[0]
-        g2 = g.flatten(2)                                  # (N, n_out, P)
-        w2 = weight.reshape(n_out, 128).float()
-        g_feat = torch.matmul(w2.t(), g2).view_as(feat).to(feat.dtype) if ctx.needs_input_grad[0] else None
-        g_w = torch.einsum("nop,nip->oi", g2, feat.flatten(2).float()).view_as(weight).to(weight.dtype) if ctx.needs_input_grad[1] else None
-        g_b = g2.sum((0, 2)) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        dt = feat.dtype
+        g2 = g.flatten(2)                                  # (N, n_out, P) fp32
+        gh = g2.to(dt)
+        g_feat = g_w = g_b = None
+        if ctx.needs_input_grad[0]:
+            g_feat = torch.matmul(weight.detach().reshape(n_out, 128).to(dt).t(), gh).view_as(feat)
+        if ctx.needs_input_grad[1]:
+            g_w = torch.matmul(gh, feat.flatten(2).transpose(1, 2)).float().sum(0).view_as(weight).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            g_b = g2.sum((0, 2))
         return g_feat, g_w, g_b, None
 
 

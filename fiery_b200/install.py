@@ -91,6 +91,23 @@ def install(level: str = "fused"):
     return fiery_mod.Fiery
 
 
+def use_tensor_core_depth_layer(model):
+    """Replace ``model.encoder.depth_layer`` (``nn.Conv2d(128, D + C, 1)``, fiery/models/encoder.py:36) of a ``Fiery`` instance by
+    ``fiery_b200.depth_layer.DepthLayer`` sharing the same Parameters (``state_dict`` keys unchanged): under autocast the backbone's
+    half features go straight to an fp32 head tensor, the dtype the lift computes in.  Returns the model; layers the kernel does not
+    cover (input channels != 128, more than 128 outputs) are left alone with one warning."""
+    from .depth_layer import DepthLayer
+    conv = model.encoder.depth_layer
+    if isinstance(conv, DepthLayer):
+        return model
+    if conv.in_channels != 128 or conv.out_channels > 128 or conv.kernel_size != (1, 1):
+        _warn_once(("depth_layer", conv.in_channels, conv.out_channels),
+                   f"fiery_b200: depth_layer {conv.in_channels}->{conv.out_channels} not covered by the tensor-core kernel; left as is")
+        return model
+    model.encoder.depth_layer = DepthLayer.from_conv(conv)
+    return model
+
+
 def uninstall():
     if not _saved:
         return

@@ -26,6 +26,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .depth_layer import DepthLayer
 from .lift import LiftSplat, pack_sequence_dim, unpack_sequence_dim
 from .synthetic import LiftConfig, make_calibration, make_egomotion, shard_frames
 
@@ -108,6 +109,8 @@ class LiftTrainModel(nn.Module):
         super().__init__()
         self.cfg, self.feature_input = cfg, feature_input
         self.encoder = StandInEncoder(cfg.depth_bins, cfg.out_channels, cfg.use_depth_distribution)
+        # the head tensor's producer on the tensor cores: half features in (AMP), fp32 head out -- no widening pass before the lift
+        self.encoder.depth_layer = DepthLayer.from_conv(self.encoder.depth_layer)
         self.lift = LiftSplat.from_config(cfg, output_layout="channels_last")     # the BEV convs consume channels-last: no layout pass
         self.head = BevHead(cfg.out_channels)
         self.segmentation_weight = nn.Parameter(torch.tensor(0.0))

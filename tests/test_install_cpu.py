@@ -97,3 +97,35 @@ def test_unsupported_configuration_runs_the_reference_method(fake_fiery):
             m.calculate_birds_eye_view_features(x, torch.eye(3).expand(1, 1, 6, 3, 3), torch.eye(4).expand(1, 1, 6, 4, 4))
     finally:
         fb.uninstall()
+
+
+def test_depth_layer_swap_keeps_parameters_and_state_dict_keys():
+    """use_tensor_core_depth_layer: Encoder.depth_layer (encoder.py:36) becomes the tcgen05 layer with the SAME Parameters."""
+    import types
+    import torch.nn as nn
+    import fiery_b200.install as fb
+    from fiery_b200.depth_layer import DepthLayer
+    model = types.SimpleNamespace(encoder=nn.Module())
+    conv = nn.Conv2d(128, 48 + 64, kernel_size=1, padding=0)
+    model.encoder.depth_layer = conv
+    keys = set(model.encoder.state_dict())
+    assert fb.use_tensor_core_depth_layer(model) is model
+    layer = model.encoder.depth_layer
+    assert isinstance(layer, DepthLayer) and layer.weight is conv.weight and layer.bias is conv.bias
+    assert set(model.encoder.state_dict()) == keys == {"depth_layer.weight", "depth_layer.bias"}
+    assert fb.use_tensor_core_depth_layer(model).encoder.depth_layer is layer          # idempotent
+    other = types.SimpleNamespace(encoder=nn.Module())
+    other.encoder.depth_layer = nn.Conv2d(64, 112, kernel_size=1)
+    with pytest.warns(RuntimeWarning, match="not covered"):
+        fb.use_tensor_core_depth_layer(other)
+    assert isinstance(other.encoder.depth_layer, nn.Conv2d)
+    fb._warned.clear()
+
+
+def test_depth_layer_has_no_cpu_path():
+    import torch
+    from fiery_b200.depth_layer import DepthLayer
+    with pytest.raises(Exception, match="CUDA|cuda"):
+        DepthLayer(112)(torch.zeros(1, 128, 4, 8))
+    with pytest.raises(ValueError):
+        DepthLayer(200)

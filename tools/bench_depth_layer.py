@@ -23,7 +23,8 @@ def timeit(fn, iters=30):
     return t[len(t) // 2] * 1e3
 
 
-for dtype in (torch.float16, torch.bfloat16, torch.float32):
+only = sys.argv[2] if len(sys.argv) > 2 else None
+for dtype in ((torch.float16,) if only == 'fp16' else (torch.float16, torch.bfloat16, torch.float32)):
     feat = torch.randn(N, 128, h, w, device=dev).to(dtype)
     weight = torch.randn(n_out, 128, 1, 1, device=dev) * 0.1
     bias = torch.randn(n_out, device=dev)
@@ -32,7 +33,7 @@ for dtype in (torch.float16, torch.bfloat16, torch.float32):
     torch.backends.cudnn.allow_tf32 = True
     wp = pack_weight(weight, dtype)
     t_ours = timeit(lambda: depth_layer_forward(feat, weight, bias, wp))
-    t_conv = timeit(lambda: F.conv2d(feat, wd, bd))
-    t_conv_widen = timeit(lambda: F.conv2d(feat, wd, bd).float())
+    t_conv = timeit(lambda: F.conv2d(feat, wd, bd)) if only is None else 0.0
+    t_conv_widen = timeit(lambda: F.conv2d(feat, wd, bd).float()) if only is None else 0.0
     byts = feat.numel() * feat.element_size() + N * n_out * h * w * 4
     print(f"{dtype}: tcgen05 {t_ours:.1f} us ({byts / t_ours * 1e-3:.0f} GB/s algorithmic) | cuDNN {t_conv:.1f} us | cuDNN + .float() {t_conv_widen:.1f} us")

@@ -4,6 +4,7 @@
     python tools/ncu_target.py <workload> tile_planned   # the same with a caller-owned geometry plan (planned variant of the kernel)
     python tools/ncu_target.py <workload> step    # the NCHW step (tile kernels + layout passes of every frame group), 4 calls
     python tools/ncu_target.py <workload> bwd     # NCHW backward (re-layout + backward tile kernel), 3 calls
+    python tools/ncu_target.py <workload> depth   # the tcgen05 depth_layer (fp16 features -> fp32 head tensor) at the workload's size, 4 calls
     python tools/ncu_target.py <workload> conv    # the tcgen05 first BEV convolution on a channel-last BEV of the workload's size, 4 calls
 """
 import os, sys
@@ -25,7 +26,16 @@ K_d, E_d = torch.from_numpy(K).to(dev), torch.from_numpy(E).to(dev)
 lift = LiftSplat.from_config(cfg).to(dev)
 c = lift._constants(dev)
 X, Y = cfg.bev_hw
-if mode == "conv":
+if mode == "depth":
+    from fiery_b200.depth_layer import depth_layer_forward, pack_weight as pack_depth
+    fh, fw = cfg.feat_hw
+    feat = torch.randn(cfg.frames * cfg.n_cameras, 128, fh, fw, device=dev).half()
+    w = torch.randn(cfg.head_channels, 128, 1, 1, device=dev) * 0.05
+    b = torch.randn(cfg.head_channels, device=dev)
+    wp = pack_depth(w, torch.float16)
+    for _ in range(4):
+        depth_layer_forward(feat, w, b, wp)
+elif mode == "conv":
     from fiery_b200.bev_conv import first_conv_forward, pack_weight
     xb = torch.randn(cfg.frames, X, Y, 64, device=dev).permute(0, 3, 1, 2)
     wp = pack_weight(torch.randn(64, 64, 7, 7, device=dev) * 0.02)
