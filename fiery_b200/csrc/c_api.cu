@@ -136,6 +136,7 @@ int encode_bev_map(CUtensorMap* map, float* bev, long long pillars, int channels
 
 // launchers defined next to their kernels
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, void* scratch, const void* plan,
+                        const float* warp_theta, const unsigned char* warp_copy,
                         cudaStream_t);
 int launch_lift_plan(const LiftParams& P, unsigned char* tiles, unsigned char* touched, int want_streams, cudaStream_t stream);
 int lift_chunk_frames(const LiftParams& P);
@@ -260,7 +261,19 @@ FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head
     if (rc != FIERY_OK) return rc;
     if (P.n_frames == 0) return FIERY_OK;
     FIERY_REQUIRE(head && bev_out, "head / bev_out is NULL");
-    return launch_lift_forward(P, head, desc->head_dtype, bev_out, scratch, plan, static_cast<cudaStream_t>(stream));
+    return launch_lift_forward(P, head, desc->head_dtype, bev_out, scratch, plan, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+FIERY_API int fiery_lift_forward_warped(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
+                                        const float* frustum_u, const float* frustum_v, const float* frustum_d, float* bev_out,
+                                        void* scratch, const void* plan, const float* theta, const uint8_t* copy_mask, void* stream) {
+    LiftParams P;
+    int rc = make_params(desc, calib_a, calib_b, frustum_u, frustum_v, frustum_d, P);
+    if (rc != FIERY_OK) return rc;
+    if (P.n_frames == 0) return FIERY_OK;
+    FIERY_REQUIRE(head && bev_out && theta && copy_mask, "head / bev_out / theta / copy_mask is NULL");
+    FIERY_REQUIRE(desc->bev_layout == FIERY_BEV_NCHW, "the warped lift writes the NCHW layout only");
+    return launch_lift_forward(P, head, desc->head_dtype, bev_out, scratch, plan, theta, copy_mask, static_cast<cudaStream_t>(stream));
 }
 
 FIERY_API int fiery_lift_forward_timed(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,

@@ -8,6 +8,7 @@
 #include <mutex>
 
 #include "lift_plan.cuh"
+#include "warp_sample.cuh"
 
 namespace fiery {
 
@@ -145,6 +146,98 @@ finalize_tma_kernel(const __grid_constant__ CUtensorMap bev_map, float* __restri
         if (clear_marks) *mark = 0;             // marks of a caller-owned plan stay: the plan is reused
     }
     if (tid == 0 || row) tma_store_commit_and_wait();   // the shared sources must outlive the copies
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Layout pass with the warp of cumulative_warp_features folded in (fiery/models/fiery.py:143-146,
+// fiery/utils/geometry.py:181-253): instead of transposing the channel-last accumulator of a frame into the NCHW output and letting
+// a second kernel re-read it, every OUTPUT pixel of the frame gathers its (up to) four bilinear neighbours straight from the
+// accumulator -- whose 256-byte channel rows are exactly what a gather wants -- and the blended pixel goes to the NCHW output.
+// Present frames (copy flag) take their own pillar with weight one: bit-identical to the plain layout pass.  Sample positions
+// and the blend order are those of warp_forward_kernel (warp_sample.cuh).  A quarter-warp serves one output pixel (lane = two
+// 16-byte pieces of the channel row: one full 128-byte line per quarter and load instruction), four neighbours are fetched
+// before the first use; pillars that received no point (mark byte clear) are not read.  The (64 pixels x 64 channels) block is
+// turned through padded shared memory (conflict-free both ways) so that every store instruction writes 128 contiguous bytes of a
+// channel plane.  A source pillar is read by several CTAs, so the accumulator cannot be cleared here: clear_touched_kernel
+// restores the all-zero scratch afterwards.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FW_P = 64;
+constexpr int FW_THREADS = 256;
+__global__ void __launch_bounds__(FW_THREADS)
+finalize_warp_kernel(const float* __restrict__ accum, const unsigned char* __restrict__ touched, float* __restrict__ bev,
+                     long long pillars, int H, int W, int tiles_per_frame, int frame_out0, const float* __restrict__ theta,
+                     const unsigned char* __restrict__ copy_mask) {
+    constexpr int C = 64;
+    __shared__ float s_out[C][FW_P + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x / tiles_per_frame;
+    const long long p0 = static_cast<long long>(blockIdx.x % tiles_per_frame) * FW_P;
+    const int gframe = frame_out0 + frame;
+    const float* acc_f = accum + static_cast<size_t>(frame) * pillars * C;
+    const unsigned char* tch = touched + static_cast<size_t>(frame) * pillars;
+    const int l = lane & 7, q = lane >> 3;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int pxl = pass * 32 + warp * 4 + q;
+        const long long pix = p0 + pxl;
+        float4 a[4], b[4];
+        float w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            b[k] = a[k];
+            w[k] = 0.f;
+        }
+        if (pix < pillars) {
+            const SamplePos s = make_sample(theta, copy_mask, gframe, static_cast<int>(pix), W, H, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w[k] = s.w[k];
+                if (s.ok[k] && tch[s.off[k]]) {
+                    const float4* row = reinterpret_cast<const float4*>(acc_f + static_cast<size_t>(s.off[k]) * C);
+                    a[k] = __ldg(row + l);
+                    b[k] = __ldg(row + 8 + l);
+                }
+            }
+        }
+        // the blend of warp_forward_kernel: w0*v0, then fma with neighbours 1..3
+        float4 ra, rb;
+#define FIERY_BLEND(f) \
+        ra.f = fmaf(w[3], a[3].f, fmaf(w[2], a[2].f, fmaf(w[1], a[1].f, w[0] * a[0].f))); \
+        rb.f = fmaf(w[3], b[3].f, fmaf(w[2], b[2].f, fmaf(w[1], b[1].f, w[0] * b[0].f)));
+        FIERY_BLEND(x) FIERY_BLEND(y) FIERY_BLEND(z) FIERY_BLEND(w)
+#undef FIERY_BLEND
+        s_out[4 * l + 0][pxl] = ra.x; s_out[4 * l + 1][pxl] = ra.y; s_out[4 * l + 2][pxl] = ra.z; s_out[4 * l + 3][pxl] = ra.w;
+        s_out[32 + 4 * l + 0][pxl] = rb.x; s_out[32 + 4 * l + 1][pxl] = rb.y; s_out[32 + 4 * l + 2][pxl] = rb.z; s_out[32 + 4 * l + 3][pxl] = rb.w;
+    }
+    __syncthreads();
+    float* dst = bev + static_cast<size_t>(gframe) * C * pillars + p0;
+#pragma unroll
+    for (int cc = 0; cc < C / (FW_THREADS / 32); ++cc) {
+        const int c = warp * (C / (FW_THREADS / 32)) + cc;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int px = half * 32 + lane;
+            if (p0 + px < pillars) __stcs(dst + static_cast<size_t>(c) * pillars + px, s_out[c][px]);
+        }
+    }
+}
+
+// Restores the all-zero scratch after finalize_warp_kernel: a warp looks at 32 marks and zeroes the 256-byte accumulator row of
+// every marked pillar with one 8-byte store per lane; marks that live in the scratch are cleared too (a caller's plan keeps its own).
+__global__ void __launch_bounds__(256)
+clear_touched_kernel(float* __restrict__ accum, unsigned char* __restrict__ touched, long long n_pillars, int clear_marks) {
+    const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const unsigned char f = p < n_pillars ? touched[p] : 0;
+    unsigned m = __ballot_sync(0xffffffffu, f != 0);
+    const long long base = p - lane;
+    while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        reinterpret_cast<float2*>(accum + static_cast<size_t>(base + i) * 64)[lane] = make_float2(0.f, 0.f);
+    }
+    if (f && clear_marks) touched[p] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -290,14 +383,17 @@ static inline void timer_end(cudaStream_t st) {
     }
 }
 
+// warp_theta != NULL: the layout pass samples every frame under its (2, 3) affine map (frames flagged in warp_copy pass through) --
+// the lift followed by cumulative_warp_features in one chain; NCHW output only
 int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, float* bev_out, void* scratch, const void* plan,
-                        cudaStream_t stream) {
+                        const float* warp_theta, const unsigned char* warp_copy, cudaStream_t stream) {
     FIERY_REQUIRE(head_dtype == FIERY_DTYPE_F32 || head_dtype == FIERY_DTYPE_F16, "head dtype %d not supported (fp32 / fp16)", head_dtype);
     FIERY_REQUIRE(P.C == 64, "channels=%d not supported by this build (C must be 64)", P.C);
     FIERY_REQUIRE(P.D >= 1 && P.D <= 48, "depth_bins=%d not supported by this build (1..48)", P.D);
     FIERY_REQUIRE(P.ww % 4 == 0, "feat_w=%d must be a multiple of 4 (TMA row pitch must be 16-byte aligned)", P.ww);
     FIERY_REQUIRE(P.hh <= PLAN_MAX_ROWS, "feat_h=%d not supported by this build (<= %d)", P.hh, PLAN_MAX_ROWS);
     const bool nchw = P.bev_layout == FIERY_BEV_NCHW;
+    FIERY_REQUIRE(!warp_theta || nchw, "the warped lift writes the NCHW layout only");
     FIERY_REQUIRE(scratch != nullptr || !nchw, "NCHW output needs the zeroed scratch buffer of fiery_lift_scratch_bytes()");
     int rc = FIERY_OK;
     LiftParams Q = P;
@@ -313,7 +409,7 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
     unsigned char* scratch_marks = nchw ? reinterpret_cast<unsigned char*>(accum + static_cast<size_t>(chunk) * P.pillars * P.C) : nullptr;
     const bool tma_pass = P.pillars % 4 == 0;      // the output map needs a 16-byte row pitch
     CUtensorMap bev_map;
-    if (nchw && tma_pass) {
+    if (nchw && tma_pass && !warp_theta) {
         rc = encode_bev_map(&bev_map, bev_out, P.pillars, P.C, P.n_frames, FT_P);
         if (rc != FIERY_OK) return rc;
     }
@@ -356,7 +452,13 @@ int launch_lift_forward(const LiftParams& P, const void* head, int head_dtype, f
             if (rc != FIERY_OK) return rc;
             if (nchw) {
                 timer_begin(st, 2);
-                if (tma_pass) {
+                if (warp_theta) {
+                    const int tpf = static_cast<int>((P.pillars + FW_P - 1) / FW_P);
+                    finalize_warp_kernel<<<static_cast<unsigned>(tpf) * Q.n_frames, FW_THREADS, 0, st>>>(
+                        Q.accum, marks, bev_out, P.pillars, P.grid.X, P.grid.Y, tpf, Q.frame0, warp_theta, warp_copy);
+                    const long long n = P.pillars * Q.n_frames;
+                    clear_touched_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(Q.accum, marks, n, plan ? 0 : 1);
+                } else if (tma_pass) {
                     const int tpf = static_cast<int>((P.pillars + FT_P - 1) / FT_P);
                     finalize_tma_kernel<<<static_cast<unsigned>(tpf) * Q.n_frames, FT_THREADS, 0, st>>>(bev_map, Q.accum, marks, P.pillars,
                                                                                                      tpf, Q.frame0, plan ? 0 : 1);

@@ -206,6 +206,28 @@ class LiftSplat(nn.Module):
         bev, _plan = torch.ops.fiery_b200.lift_splat(head, intrinsics, extrinsics, plan, ops.register_module(self, head.device), make_plan)
         return bev
 
+    def forward_warped(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor, flow: torch.Tensor,
+                       spatial_extent, plan: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The lift followed by ``cumulative_warp_features(bev.clone(), flow, mode='bilinear', spatial_extent=...)``
+        (fiery.py:140-146) as ONE chain: ``flow`` (b, s, 6) is the sequence's egomotion, ``intrinsics`` / ``extrinsics`` are
+        (b*s, n, ...), ``head`` (b*s*n, D+C, h, w); returns (b, s, C, X, Y) float32 contiguous.  The layout pass gathers the
+        bilinear neighbours of every output pixel straight from the channel-last accumulator (fiery_lift_forward_warped), so the
+        unwarped BEV is never written.  Backward: the warp's adjoint, then the lift's backward (one shared plan)."""
+        from .warp import _device_theta
+        _require_cuda(head, "head")
+        b, s = flow.shape[:2]
+        if intrinsics.shape[0] != b * s:
+            raise ValueError(f"flow is (b={b}, s={s}, 6) but the calibrations hold {intrinsics.shape[0]} frames")
+        if s == 1:                                         # identity, like the reference (geometry.py:237)
+            return self.forward(head, intrinsics, extrinsics, plan).unflatten(0, (b, s)).contiguous()
+        if flow.shape[1] < 2:
+            raise IndexError("flow needs at least two timesteps")
+        theta, copy_mask = _device_theta(flow.to(head.device), spatial_extent, cumulative=True)
+        if plan is None and torch.is_grad_enabled() and head.requires_grad:
+            plan = self.plan(intrinsics, extrinsics)
+        bev = _LiftWarpedFn.apply(head, intrinsics, extrinsics, plan, theta, copy_mask, self)
+        return bev.unflatten(0, (b, s))
+
     def plan(self, intrinsics: torch.Tensor, extrinsics: torch.Tensor) -> torch.Tensor:
         """The geometry plan of a batch of calibrations (fiery_lift_plan): where every frustum point lands -- get_geometry
         (fiery.py:193-208) + voxel index / mask / rank (fiery.py:236-256) -- as pillar runs, in a device byte tensor.  Valid for
@@ -346,7 +368,10 @@ class LiftSplat(nn.Module):
 
     # -- raw launches (used by the autograd function and by bench.py) ------------------------------------------------
     def _launch_forward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
-                        scratch: Optional[torch.Tensor] = None, plan: Optional[torch.Tensor] = None) -> torch.Tensor:
+                        scratch: Optional[torch.Tensor] = None, plan: Optional[torch.Tensor] = None,
+                        warp: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+        """``warp``: (theta (B', 2, 3), copy_mask (B',) uint8) -- the layout pass samples every frame under its map
+        (fiery_lift_forward_warped); NCHW output only."""
         _require_cuda(head, "head")
         lib = _lib.load()
         dev = head.device
@@ -365,7 +390,7 @@ class LiftSplat(nn.Module):
         X, Y, _ = c["dim"]
         pooled = 0
         with torch.cuda.device(dev):
-            if self.output_layout == "channels_last":
+            if self.output_layout == "channels_last" and warp is None:
                 desc = self._desc(c, B, n, head.dtype, mode, _lib.BEV_NHWC)
                 store = torch.zeros((B, X, Y, C), dtype=torch.float32, device=dev)
                 out = store.permute(0, 3, 1, 2)
@@ -375,16 +400,25 @@ class LiftSplat(nn.Module):
                 out = store
             if plan is not None and plan.numel() < int(lib.fiery_lift_plan_bytes(desc)):
                 raise ValueError("plan was made for another batch shape: rebuild it with LiftSplat.plan(intrinsics, extrinsics)")
-            if scratch is None and B and self.output_layout != "channels_last":
+            if scratch is None and B and (self.output_layout != "channels_last" or warp is not None):
                 pooled = int(lib.fiery_lift_scratch_bytes(desc))
                 scratch = _scratch.get(dev, pooled)            # zero-filled once; the kernels leave it zeroed again
             scratch_ptr = scratch.data_ptr() if (B and scratch is not None) else 0
-            status = lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
-                                            c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
-                                            plan.data_ptr() if plan is not None else 0, _stream_ptr(dev))
+            if warp is None:
+                status = lib.fiery_lift_forward(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
+                                                c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
+                                                plan.data_ptr() if plan is not None else 0, _stream_ptr(dev))
+            else:
+                theta, copy_mask = warp
+                if theta.numel() != B * 6 or copy_mask.numel() != B or theta.dtype != torch.float32 or copy_mask.dtype != torch.uint8:
+                    raise ValueError("warp must be (theta (B', 2, 3) float32, copy_mask (B',) uint8) for the B' frames of this call")
+                status = lib.fiery_lift_forward_warped(desc, head.data_ptr(), a.data_ptr(), b.data_ptr(), c["u"].data_ptr(),
+                                                       c["v"].data_ptr(), c["d"].data_ptr(), store.data_ptr(), scratch_ptr,
+                                                       plan.data_ptr() if plan is not None else 0, theta.data_ptr(),
+                                                       copy_mask.data_ptr(), _stream_ptr(dev))
             if status != 0 and pooled:
                 _scratch.discard(dev, pooled)          # a launch sequence that stopped half way may have left it dirty
-            _lib.check(status, "fiery_lift_forward")
+            _lib.check(status, "fiery_lift_forward_warped" if warp is not None else "fiery_lift_forward")
         return out
 
     def _launch_backward(self, head: torch.Tensor, intrinsics: torch.Tensor, extrinsics: torch.Tensor,
@@ -413,6 +447,34 @@ class LiftSplat(nn.Module):
                                                plan.data_ptr() if plan is not None else 0, _stream_ptr(dev)),
                        "fiery_lift_backward")
         return grad_head
+
+
+class _LiftWarpedFn(torch.autograd.Function):
+    """Fused forward (lift + warp epilogue); backward = adjoint of the warp (fiery_warp_features_backward), then the lift's backward."""
+
+    @staticmethod
+    def forward(ctx, head, intrinsics, extrinsics, plan, theta, copy_mask, module):
+        ctx.module = module
+        ctx.save_for_backward(head, intrinsics, extrinsics, theta, copy_mask, plan if plan is not None else torch.empty(0, device=head.device))
+        ctx.has_plan = plan is not None
+        return module._launch_forward(head.detach(), intrinsics, extrinsics, plan=plan, warp=(theta, copy_mask))
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        head, intrinsics, extrinsics, theta, copy_mask, plan = ctx.saved_tensors
+        lib = _lib.load()
+        g = grad_out.float().contiguous()
+        n, C, H, W = g.shape
+        g_bev = torch.zeros_like(g)
+        with torch.cuda.device(g.device):
+            _lib.check(lib.fiery_warp_features_backward(n, C, H, W, g.data_ptr(), C * H * W, theta.data_ptr(), copy_mask.data_ptr(),
+                                                        g_bev.data_ptr(), C * H * W, 0, _stream_ptr(g.device)),
+                       "fiery_warp_features_backward")
+        h32 = head.detach()
+        if h32.dtype != torch.float32:
+            h32 = h32.float()
+        g_head = ctx.module._launch_backward(h32, intrinsics, extrinsics, g_bev, plan if ctx.has_plan else None)
+        return g_head.to(head.dtype), None, None, None, None, None, None
 
 
 class GraphedLift:
@@ -447,12 +509,8 @@ class GraphedLift:
         return self.output
 
 
-def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):
-    """Replacement for ``Fiery.calculate_birds_eye_view_features`` (fiery/models/fiery.py:275-286), same signature:
-    x (b, s, n, 3, H, W), intrinsics (b, s, n, 3, 3), extrinsics (b, s, n, 4, 4) -> (b, s, C, X, Y).
-
-    ``self`` is the reference ``Fiery`` module; its backbone and ``depth_layer`` (library convolutions,
-    encoder.py:94-96) run unchanged, everything after them runs in the fused CUDA lift."""
+def _head_and_lift(self, x, intrinsics, extrinsics):
+    """The part of fiery.py:275-286 in front of the lift: backbone + depth_layer on the packed cameras, and this model's LiftSplat."""
     b, s, n, c, h, w = x.shape
     x = pack_sequence_dim(x)
     intrinsics = pack_sequence_dim(intrinsics)
@@ -463,5 +521,29 @@ def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):
     if lift is None:
         lift = LiftSplat.from_fiery(self)          # shares the model's Parameters; device-side constants follow them
         object.__setattr__(self, "_fiery_b200_lift", lift)
+    return head, intrinsics, extrinsics, lift
+
+
+def calculate_birds_eye_view_features(self, x, intrinsics, extrinsics):
+    """Replacement for ``Fiery.calculate_birds_eye_view_features`` (fiery/models/fiery.py:275-286), same signature:
+    x (b, s, n, 3, H, W), intrinsics (b, s, n, 3, 3), extrinsics (b, s, n, 4, 4) -> (b, s, C, X, Y).
+
+    ``self`` is the reference ``Fiery`` module; its backbone and ``depth_layer`` (library convolutions,
+    encoder.py:94-96) run unchanged, everything after them runs in the fused CUDA lift."""
+    b, s = x.shape[:2]
+    head, intrinsics, extrinsics, lift = _head_and_lift(self, x, intrinsics, extrinsics)
     bev = lift(head, intrinsics, extrinsics)
     return unpack_sequence_dim(bev, b, s)
+
+
+def birds_eye_view_features_warped(self, x, intrinsics, extrinsics, future_egomotion):
+    """``Fiery.forward``'s two statements fiery.py:140-146 in one call:
+
+        x = self.calculate_birds_eye_view_features(image, intrinsics, extrinsics)
+        x = cumulative_warp_features(x.clone(), future_egomotion, mode='bilinear', spatial_extent=self.spatial_extent)
+
+    -> (b, s, C, X, Y): the past frames' BEV features in the present frame's reference, the present frame as is.  The warp runs
+    as the lift's layout pass (``LiftSplat.forward_warped``), so the unwarped BEV is never materialised; INTEGRATION.md shows the
+    two-line patch of ``Fiery.forward``."""
+    head, intrinsics, extrinsics, lift = _head_and_lift(self, x, intrinsics, extrinsics)
+    return lift.forward_warped(head, intrinsics, extrinsics, future_egomotion, tuple(float(v) for v in self.spatial_extent))

@@ -125,6 +125,18 @@ FIERY_API int fiery_lift_forward(const fiery_lift_desc_t* desc, const void* head
                        const float* frustum_u, const float* frustum_v, const float* frustum_d,
                        float* bev_out, void* scratch, const void* plan, void* stream);
 
+/*
+ * The lift followed by cumulative_warp_features (fiery/models/fiery.py:140-146, fiery/utils/geometry.py:225-253) in one chain: same
+ * arguments as fiery_lift_forward (bev_layout must be FIERY_BEV_NCHW), plus the sampling maps of fiery_warp_theta for the B' frames:
+ * theta (B', 2, 3) fp32 and copy_mask (B') bytes (1 = the present frame of its sequence: written as is, geometry.py:243).  Frame f of
+ * bev_out is the bilinear sample (affine_grid + grid_sample, zero padding, align_corners=False) of frame f's lifted features --
+ * gathered straight from the channel-last accumulator by the layout pass, so the unwarped BEV is never written or re-read
+ * (3 launches per frame group instead of 2, and none of the standalone warp's).  [SURVEY.md section 8f, next-1]
+ */
+FIERY_API int fiery_lift_forward_warped(const fiery_lift_desc_t* desc, const void* head, const float* calib_a, const float* calib_b,
+                                        const float* frustum_u, const float* frustum_v, const float* frustum_d, float* bev_out,
+                                        void* scratch, const void* plan, const float* theta, const uint8_t* copy_mask, void* stream);
+
 /* Number of kernel launches one fiery_lift_forward call with this descriptor issues (NHWC: the tile kernel; NCHW: tile kernel
  * + layout pass per frame group; groups of frames run as concurrent chains on internal streams that are forked from and
  * joined back into `stream` with events, so the call behaves like work queued on `stream` and can be captured in a graph). */
