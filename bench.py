@@ -614,6 +614,27 @@ def main():
                 t_wr = timed_steps(lambda: WO.cumulative_warp_features(xw.clone(), fl, mode="bilinear", spatial_extent=ext), 5)
             warp_extra["reference_ops_on_gpu_ms"] = float(np.mean(t_wr))
         del out_w
+        # lift + warp as one chain (fiery_lift_forward_warped) against the two public calls, on this run's own frames
+        seq = 3 if frames % 3 == 0 else (2 if frames % 2 == 0 else 0)
+        if seq and args.layout != "channels_last":
+            fb_ = frames // seq
+            fl2 = torch.from_numpy(make_egomotion(fb_, seq, seed=11)).to(dev)
+            head32 = head_d.float()
+            with torch.no_grad():
+                def unfused():
+                    return cumulative_warp_features(lift(head32, K_d, E_d).unflatten(0, (fb_, seq)), fl2, mode="bilinear", spatial_extent=ext)
+
+                def fused():
+                    return lift.forward_warped(head32, K_d, E_d, fl2, ext)
+                for _ in range(3):
+                    unfused(); fused()
+                u_ms = float(np.mean(timed_steps(unfused, S)))
+                f_ms = float(np.mean(timed_steps(fused, S)))
+            warp_extra["lift_plus_warp"] = {"frames": frames, "sequence": seq, "unfused_ms": u_ms, "fused_ms": f_ms,
+                                            "what": "eager public calls on this run's head tensor: LiftSplat.forward + "
+                                                    "cumulative_warp_features (two passes over the BEV) vs LiftSplat.forward_warped "
+                                                    "(the warp is the lift's layout pass); L2 flushed before every call"}
+            del head32
 
     # ---- next row: Decoder.first_conv 7x7 s2 64->64 on tcgen05, fed by the channel-last lift output ------
     conv_extra = None

@@ -3,6 +3,7 @@
     python tools/ncu_target.py <workload> tile    # the column tile kernel alone (channel-last target), whole batch, 4 launches
     python tools/ncu_target.py <workload> tile_planned   # the same with a caller-owned geometry plan (planned variant of the kernel)
     python tools/ncu_target.py <workload> step    # the NCHW step (tile kernels + layout passes of every frame group), 4 calls
+    python tools/ncu_target.py <workload> step_warped   # lift with the warp folded into the layout pass (finalize_warp_kernel), 3 calls
     python tools/ncu_target.py <workload> bwd     # NCHW backward (re-layout + backward tile kernel), 3 calls
     python tools/ncu_target.py <workload> depth   # the tcgen05 depth_layer (fp16 features -> fp32 head tensor) at the workload's size, 4 calls
     python tools/ncu_target.py <workload> conv    # the tcgen05 first BEV convolution on a channel-last BEV of the workload's size, 4 calls
@@ -41,6 +42,12 @@ elif mode == "conv":
     wp = pack_weight(torch.randn(64, 64, 7, 7, device=dev) * 0.02)
     for _ in range(4):
         first_conv_forward(xb, wp)
+elif mode == "step_warped":
+    from fiery_b200.synthetic import make_egomotion
+    seq = 3 if cfg.frames % 3 == 0 else 2
+    fl = torch.from_numpy(make_egomotion(cfg.frames // seq, seq, seed=11)).to(dev)
+    for _ in range(3):
+        lift.forward_warped(head, K_d, E_d, fl, (float(cfg.x_bound[1]), float(cfg.y_bound[1])))
 elif mode == "bwd":
     g = torch.from_numpy(make_grad_bev(cfg, seed=100)).to(dev)
     for _ in range(3):
