@@ -600,8 +600,17 @@ def main():
         for _ in range(3):
             warp_kernel_only()
         wk_ms = float(np.mean(timed_steps(warp_kernel_only, S)))
+        gx_w = torch.empty_like(xw)
+
+        def warp_backward_only():                                       # gather adjoint (+ the scatter launch that exits at once)
+            _lib.check(lib.fiery_warp_features_backward(wb * ws, cfg.out_channels, X, Y, out_w.data_ptr(), chw, th_w.data_ptr(),
+                                                        mask_w.data_ptr(), gx_w.data_ptr(), chw, 0, stream), "warp backward")
+        for _ in range(3):
+            warp_backward_only()
+        wkb_ms = float(np.mean(timed_steps(warp_backward_only, S)))
         warp_extra = {"frames": wb * ws, "ms_per_call": w_ms, "frames_per_s": wb * ws / (w_ms * 1e-3),
                       "algorithmic_bytes": w_bytes, "kernel_ms": wk_ms, "achieved_gbs": w_bytes / (wk_ms * 1e-3) / 1e9,
+                      "backward_ms": wkb_ms, "backward_achieved_gbs": w_bytes / (wkb_ms * 1e-3) / 1e9,
                       "what": "fiery_b200.warp.cumulative_warp_features, (3, 3, 64, X, Y) fp32: ms_per_call = the eager "
                               "public call (pose-algebra kernel + sampling kernel + output allocation), kernel_ms / "
                               "achieved_gbs = warp_forward_kernel alone via fiery_warp_features_forward; L2 flushed "
@@ -613,7 +622,7 @@ def main():
                     WO.cumulative_warp_features(xw.clone(), fl, mode="bilinear", spatial_extent=ext)
                 t_wr = timed_steps(lambda: WO.cumulative_warp_features(xw.clone(), fl, mode="bilinear", spatial_extent=ext), 5)
             warp_extra["reference_ops_on_gpu_ms"] = float(np.mean(t_wr))
-        del out_w
+        del out_w, gx_w
         # lift + warp as one chain (fiery_lift_forward_warped) against the two public calls, on this run's own frames
         seq = 3 if frames % 3 == 0 else (2 if frames % 2 == 0 else 0)
         if seq and args.layout != "channels_last":
@@ -622,7 +631,8 @@ def main():
             head32 = head_d.float()
             with torch.no_grad():
                 def unfused():
-                    return cumulative_warp_features(lift(head32, K_d, E_d).unflatten(0, (fb_, seq)), fl2, mode="bilinear", spatial_extent=ext)
+                    return cumulative_warp_features(lift._launch_forward(head32, K_d, E_d).unflatten(0, (fb_, seq)), fl2,
+                                                    mode="bilinear", spatial_extent=ext)
 
                 def fused():
                     return lift.forward_warped(head32, K_d, E_d, fl2, ext)
@@ -630,10 +640,24 @@ def main():
                     unfused(); fused()
                 u_ms = float(np.mean(timed_steps(unfused, S)))
                 f_ms = float(np.mean(timed_steps(fused, S)))
-            warp_extra["lift_plus_warp"] = {"frames": frames, "sequence": seq, "unfused_ms": u_ms, "fused_ms": f_ms,
-                                            "what": "eager public calls on this run's head tensor: LiftSplat.forward + "
-                                                    "cumulative_warp_features (two passes over the BEV) vs LiftSplat.forward_warped "
-                                                    "(the warp is the lift's layout pass); L2 flushed before every call"}
+                # the same two call sequences captured in CUDA graphs: device time without the host's launch gaps
+                torch.cuda.synchronize()
+                g_u, g_f = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_u):
+                    keep_u = unfused()
+                with torch.cuda.graph(g_f):
+                    keep_f = fused()
+                for _ in range(3):
+                    g_u.replay(); g_f.replay()
+                ug_ms = float(np.mean(timed_steps(g_u.replay, S)))
+                fg_ms = float(np.mean(timed_steps(g_f.replay, S)))
+                del keep_u, keep_f, g_u, g_f
+            warp_extra["lift_plus_warp"] = {"frames": frames, "sequence": seq, "unfused_ms": ug_ms, "fused_ms": fg_ms,
+                                            "unfused_eager_ms": u_ms, "fused_eager_ms": f_ms,
+                                            "what": "this run's head tensor: lift (NCHW) + cumulative_warp_features (pose kernel + "
+                                                    "sampling kernel: two passes over the BEV) vs LiftSplat.forward_warped (the warp is "
+                                                    "the lift's layout pass); graph replay of the public calls, and the eager calls "
+                                                    "(host-paced); L2 flushed before every call"}
             del head32
 
     # ---- next row: Decoder.first_conv 7x7 s2 64->64 on tcgen05, fed by the channel-last lift output ------

@@ -14,13 +14,35 @@ struct SamplePos {
 
 // affine_grid (align_corners=False): normalised pixel centres x_i = (2i+1)/W - 1; grid = theta @ (x, y, 1)
 // grid_sample unnormalise (align_corners=False): ix = ((gx + 1) * W - 1) / 2
-__device__ __forceinline__ void sample_coords(const float* __restrict__ th, int i, int j, int W, int H, float& ix, float& iy) {
-    const float xs = (2.0f * i + 1.0f) / W - 1.0f;
-    const float ys = (2.0f * j + 1.0f) / H - 1.0f;
+__device__ __forceinline__ float norm_centre(int i, int n) { return (2.0f * i + 1.0f) / n - 1.0f; }
+__device__ __forceinline__ void sample_coords_norm(const float* __restrict__ th, float xs, float ys, int W, int H, float& ix, float& iy) {
     const float gx = fmaf(th[0], xs, fmaf(th[1], ys, th[2]));
     const float gy = fmaf(th[3], xs, fmaf(th[4], ys, th[5]));
     ix = ((gx + 1.0f) * W - 1.0f) * 0.5f;
     iy = ((gy + 1.0f) * H - 1.0f) * 0.5f;
+}
+__device__ __forceinline__ void sample_coords(const float* __restrict__ th, int i, int j, int W, int H, float& ix, float& iy) {
+    sample_coords_norm(th, norm_centre(i, W), norm_centre(j, H), W, H, ix, iy);
+}
+
+// The adjoint as a gather (warp_backward_gather_kernel): the output pixels that sample a given source pixel lie in a small window
+// around the inverse image of that pixel.  Inverse of the linear part of (i, j) -> (ix, iy) in pixel units, and whether the window
+// is small enough to enumerate: every map warp_features builds is a rotation (determinant 1); anything else -- strong scaling,
+// singular or non-finite maps -- takes the scatter kernel instead.  Both kernels evaluate this same predicate.
+struct InverseMap {
+    float ia, ib, ic, id;    // (i, j) = inv * ((ix, iy) - (ix0, iy0))
+    float ix0, iy0;
+    bool gather;
+};
+__device__ __forceinline__ InverseMap inverse_map(const float* __restrict__ th, int W, int H) {
+    InverseMap m;
+    const float a = th[0], b = th[1] * W / H, c = th[3] * H / W, d = th[4];
+    sample_coords(th, 0, 0, W, H, m.ix0, m.iy0);
+    const float det = a * d - b * c;
+    m.ia = d / det; m.ib = -b / det; m.ic = -c / det; m.id = a / det;
+    const float ei = fabsf(m.ia) + fabsf(m.ib), ej = fabsf(m.ic) + fabsf(m.id);
+    m.gather = fabsf(det) >= 0.25f && ei <= 4.f && ej <= 4.f && fabsf(m.ix0) < 1e6f && fabsf(m.iy0) < 1e6f;   // false for NaN / inf too
+    return m;
 }
 
 __device__ __forceinline__ SamplePos make_sample(const float* __restrict__ theta, const unsigned char* __restrict__ copy_mask,

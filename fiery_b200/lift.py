@@ -465,7 +465,7 @@ class _LiftWarpedFn(torch.autograd.Function):
         lib = _lib.load()
         g = grad_out.float().contiguous()
         n, C, H, W = g.shape
-        g_bev = torch.zeros_like(g)
+        g_bev = torch.empty_like(g)
         with torch.cuda.device(g.device):
             _lib.check(lib.fiery_warp_features_backward(n, C, H, W, g.data_ptr(), C * H * W, theta.data_ptr(), copy_mask.data_ptr(),
                                                         g_bev.data_ptr(), C * H * W, 0, _stream_ptr(g.device)),

@@ -61,7 +61,7 @@ class _WarpMaps(torch.autograd.Function):
         lib = _lib.load()
         n, C, H, W = ctx.shape
         g = _dense_maps(grad_out)
-        grad_x = torch.zeros(ctx.shape, dtype=torch.float32, device=g.device)
+        grad_x = torch.empty(ctx.shape, dtype=torch.float32, device=g.device)       # overwritten by the gather adjoint
         with torch.cuda.device(g.device):
             _lib.check(lib.fiery_warp_features_backward(n, C, H, W, g.data_ptr(), g.stride(0) if n else 0, th.data_ptr(),
                                                         mask.data_ptr() if ctx.has_mask else 0, grad_x.data_ptr(), C * H * W,

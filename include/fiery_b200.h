@@ -204,7 +204,9 @@ FIERY_API int fiery_voxels_summing_backward(int64_t n_rows, int32_t channels, co
  * if `nearest` != 0) of n_maps feature maps (C, H, W) fp32 under the affine maps theta (n_maps, 2, 3).  Map m starts at
  * x + m * x_map_stride (elements); channel planes are dense (H*W).  copy_mask (n_maps bytes, may be NULL): maps with a
  * non-zero byte are copied unchanged -- the present frame of a sequence (geometry.py:243).
- * backward: grad_x[m] += adjoint of the sampling applied to grad_out[m]; grad_x must be zero-filled (or hold a running sum).
+ * backward: grad_x[m] = adjoint of the sampling applied to grad_out[m].  grad_x is OVERWRITTEN (no zero-fill needed): the adjoint
+ * runs as a gather over the output pixels that sampled each source pixel (deterministic, no atomics); maps that are no near-rigid
+ * transforms (|det| < 1/4, strong scaling, non-finite) fall to a scatter with atomics inside the same call.
  */
 FIERY_API int fiery_warp_features_forward(int32_t n_maps, int32_t channels, int32_t height, int32_t width, const float* x,
                                           int64_t x_map_stride, const float* theta, const uint8_t* copy_mask, float* out,

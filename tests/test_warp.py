@@ -120,3 +120,70 @@ def test_gpu_pose_algebra_matches_oracle(T):
     plain, none = _device_theta(flow[:, 0].to(dev), ext, cumulative=False)
     assert none is None
     np.testing.assert_allclose(plain.cpu().numpy(), W.warp_theta(flow[:, 0], ext).numpy(), rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nearest", [0, 1])
+def test_gpu_backward_of_arbitrary_affine_maps(nearest):
+    """fiery_warp_features_backward through the C ABI for maps that are NOT the rotations warp_features builds: the gather adjoint
+    covers near-rigid maps, everything else (scaling, shear, singular, zero, non-finite) takes the scatter inside the same call;
+    grad_x is overwritten either way (it is handed in full of garbage).  Reference: autograd of affine_grid + grid_sample."""
+    import torch.nn.functional as F
+    from fiery_b200 import _lib
+    from fiery_b200.geometry import _stream_ptr
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    C, H, W = 5, 24, 40
+    th = torch.tensor([
+        [[0.96, -0.28, 0.10], [0.28, 0.96, -0.20]],        # rotation (gather)
+        [[1.00, 0.00, 0.00], [0.00, 1.00, 0.00]],          # identity (gather)
+        [[0.50, 0.00, 0.30], [0.00, 0.45, 0.00]],          # magnification: determinant < 1/4 (scatter)
+        [[3.00, 0.50, 0.00], [0.20, 2.50, 0.10]],          # minification: many outputs per source... still gather-sized
+        [[0.00, 0.00, 0.20], [0.00, 0.00, -0.30]],         # singular: every output samples one point (scatter)
+        [[1.00, 0.90, 0.00], [0.00, 1.00, 0.00]],          # shear (gather)
+        [[-0.60, 0.80, 0.00], [-0.80, -0.60, 0.50]],       # rotation by more than 90 degrees (gather)
+    ], dtype=torch.float32, device=dev)
+    n = th.shape[0]
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(n, C, H, W, generator=gen).to(dev).requires_grad_(True)
+    gout = torch.randn(n, C, H, W, generator=gen).to(dev)
+    grid = F.affine_grid(th, (n, C, H, W), align_corners=False)
+    F.grid_sample(x, grid, mode="nearest" if nearest else "bilinear", padding_mode="zeros", align_corners=False).backward(gout)
+    got = torch.full((n, C, H, W), float("nan"), device=dev)
+    _lib.check(lib.fiery_warp_features_backward(n, C, H, W, gout.data_ptr(), C * H * W, th.data_ptr(), 0, got.data_ptr(), C * H * W,
+                                                nearest, _stream_ptr(dev)), "warp backward")
+    assert torch.isfinite(got).all()
+    scale = float(x.grad.abs().max())
+    if nearest:        # a pick exactly between two pixels may flip with 1-ulp coordinate differences
+        assert float(((got - x.grad).abs() > 1e-4 * scale).float().mean()) < 5e-3
+    else:
+        assert float((got - x.grad).abs().max()) <= 1e-4 * scale
+    # a non-finite map gives a zero gradient (all of its samples are out of range), and does not disturb its neighbours
+    th2 = th.clone()
+    th2[1, 0, 0] = float("nan")
+    got2 = torch.full((n, C, H, W), float("nan"), device=dev)
+    _lib.check(lib.fiery_warp_features_backward(n, C, H, W, gout.data_ptr(), C * H * W, th2.data_ptr(), 0, got2.data_ptr(), C * H * W,
+                                                nearest, _stream_ptr(dev)), "warp backward")
+    assert float(got2[1].abs().max()) == 0.0 and torch.equal(got2[0], got[0]) and torch.equal(got2[3], got[3])
+
+
+@pytest.mark.gpu
+def test_gpu_backward_is_deterministic_at_full_size():
+    from fiery_b200.warp import cumulative_warp_features
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 3, 64, 200, 200, generator=g).to(dev).requires_grad_(True)
+    gout = torch.randn(2, 3, 64, 200, 200, generator=g).to(dev)
+    flow = torch.from_numpy(make_egomotion(2, 3, seed=4)).to(dev)
+    grads = []
+    for _ in range(2):
+        x.grad = None
+        cumulative_warp_features(x, flow, mode="bilinear", spatial_extent=(50.0, 50.0)).backward(gout)
+        grads.append(x.grad.clone())
+    assert torch.equal(grads[0], grads[1])                                  # gather adjoint: no atomics on this path
+    assert torch.equal(grads[0][:, -1], gout[:, -1])                        # the present frame's gradient passes through
+    # adjoint identity <W x, g> == <x, W^T g>
+    with torch.no_grad():
+        y = cumulative_warp_features(x.detach(), flow, mode="bilinear", spatial_extent=(50.0, 50.0))
+    lhs, rhs = float((y.double() * gout.double()).sum()), float((x.detach().double() * grads[0].double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0)

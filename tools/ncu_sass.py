@@ -8,7 +8,7 @@ out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_o
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 ie, ss, sc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Source")
-wf = hdr.index("L1 Wavefronts Shared")
+wf = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
 stalls = {n: hdr.index(n) for n in hdr if n.startswith("stall_") and "Not Issued" not in n}
 for i, r in enumerate(rows[2:]):
     n = int(r[ie] or 0)
@@ -16,4 +16,4 @@ for i, r in enumerate(rows[2:]):
         continue
     st = sorted(((int(r[j] or 0), k[6:]) for k, j in stalls.items()), reverse=True)[:2]
     st = " ".join(f"{k}:{v}" for v, k in st if v)
-    print(f"{i:5d} {n:9d} {int(r[ss] or 0):5d} {int(r[wf] or 0):9d}  {r[sc].strip():70s} {st}")
+    print(f"{i:5d} {n:9d} {int(r[ss] or 0):5d} {(int(r[wf] or 0) if wf is not None else 0):9d}  {r[sc].strip():70s} {st}")

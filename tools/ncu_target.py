@@ -3,6 +3,7 @@
     python tools/ncu_target.py <workload> tile    # the column tile kernel alone (channel-last target), whole batch, 4 launches
     python tools/ncu_target.py <workload> tile_planned   # the same with a caller-owned geometry plan (planned variant of the kernel)
     python tools/ncu_target.py <workload> step    # the NCHW step (tile kernels + layout passes of every frame group), 4 calls
+    python tools/ncu_target.py <workload> warp_bwd      # backward of cumulative_warp_features (3, 3, 64, X, Y): the gather adjoint, 3 calls
     python tools/ncu_target.py <workload> step_warped   # lift with the warp folded into the layout pass (finalize_warp_kernel), 3 calls
     python tools/ncu_target.py <workload> bwd     # NCHW backward (re-layout + backward tile kernel), 3 calls
     python tools/ncu_target.py <workload> depth   # the tcgen05 depth_layer (fp16 features -> fp32 head tensor) at the workload's size, 4 calls
@@ -42,6 +43,15 @@ elif mode == "conv":
     wp = pack_weight(torch.randn(64, 64, 7, 7, device=dev) * 0.02)
     for _ in range(4):
         first_conv_forward(xb, wp)
+elif mode == "warp_bwd":
+    from fiery_b200.synthetic import make_egomotion
+    from fiery_b200.warp import cumulative_warp_features
+    fl = torch.from_numpy(make_egomotion(3, 3, seed=7)).to(dev)
+    xw = torch.randn(3, 3, 64, X, Y, device=dev, requires_grad=True)
+    g = torch.randn(3, 3, 64, X, Y, device=dev)
+    for _ in range(3):
+        xw.grad = None
+        cumulative_warp_features(xw, fl, mode="bilinear", spatial_extent=(float(cfg.x_bound[1]), float(cfg.y_bound[1]))).backward(g)
 elif mode == "step_warped":
     from fiery_b200.synthetic import make_egomotion
     seq = 3 if cfg.frames % 3 == 0 else 2
