@@ -53,13 +53,12 @@ warp_forward_kernel(int C, int H, int W, const float* __restrict__ x, long long 
 }
 
 // Adjoint as a gather, one thread per SOURCE pixel and 32 channels: grad_x[p] = sum over the output pixels q whose sample touches p
-// of w(q, p) * grad_out[q].  The candidates q are the integer points of a small window around the inverse image of p (3x3..4x4 for
-// the rotations warp_features builds); each candidate's sample position is recomputed with the forward's own arithmetic, so a
-// candidate contributes exactly when, and with exactly the weight, the forward used p for it.  No atomics, no zero-fill of grad_x,
+// of w(q, p) * grad_out[q].  The candidates q come from the resumable window scan of warp_sample.cuh (3x3..4x4 candidates for the
+// rotations warp_features builds, at most a handful of hits); the hits of a round are collected first, then all their loads are
+// issued together -- a load inside the search loop would serialise on its latency.  No atomics, no zero-fill of grad_x,
 // deterministic; consecutive source pixels have consecutive candidates, so the loads coalesce like the forward's.
-// Maps whose window would be large (inverse_map(): strong scaling, singular, non-finite) are written as zeros here and accumulated
-// by warp_backward_scatter_kernel, which returns at once for all other maps.
 constexpr int WB_CH = 32;
+constexpr int WB_M = 6;
 template <int PLANE>
 __global__ void __launch_bounds__(WARP_THREADS, 2)
 warp_backward_gather_kernel(int C, int H, int W, const float* __restrict__ gout, long long gout_stride, const float* __restrict__ theta,
@@ -81,20 +80,14 @@ warp_backward_gather_kernel(int C, int H, int W, const float* __restrict__ gout,
         return;
     }
     const float* th = theta + map * 6;
-    const InverseMap m = inverse_map(th, W, H);
     float acc[WB_CH];
 #pragma unroll
     for (int c = 0; c < WB_CH; ++c) acc[c] = 0.f;
-    // the candidates that use this pixel are collected first (at most a handful: the pixel's 2 x 2 footprint in sample space holds
-    // about four sample points of a near-rigid map), then all their loads are issued together -- a load inside the search loop
-    // would serialise on its latency
-    constexpr int WB_M = 6;
+    AdjointScan scan = adjoint_scan_begin(inverse_map(th, W, H), pix, W, H, nearest);
     int m_off[WB_M];
     float m_w[WB_M];
-    int n_match = 0;
-#pragma unroll
-    for (int k = 0; k < WB_M; ++k) { m_off[k] = 0; m_w[k] = 0.f; }
-    auto flush = [&]() {
+    int n_match;
+    while ((n_match = adjoint_scan_next<WB_M>(scan, th, W, H, nearest, m_off, m_w)) > 0) {
 #pragma unroll
         for (int cb = 0; cb < WB_CH; cb += 8) {            // 8 channels x WB_M candidates: up to 48 loads in flight per thread
             float v[8][WB_M];
@@ -107,79 +100,10 @@ warp_backward_gather_kernel(int C, int H, int W, const float* __restrict__ gout,
 #pragma unroll
                 for (int k = 0; k < WB_M; ++k) acc[cb + c] = fmaf(m_w[k], v[c][k], acc[cb + c]);
         }
-#pragma unroll
-        for (int k = 0; k < WB_M; ++k) { m_off[k] = 0; m_w[k] = 0.f; }
-        n_match = 0;
-    };
-    if (m.gather) {
-        const int sxi = pix % W, syi = pix / W;
-        const float sx = static_cast<float>(sxi), sy = static_cast<float>(syi);
-        const float dx = sx - m.ix0, dy = sy - m.iy0;
-        const float ci = m.ia * dx + m.ib * dy, cj = m.ic * dx + m.id * dy;
-        const float r = nearest ? 0.5f : 1.0f;
-        const float slack = 0.05f + 1e-4f * (fabsf(ci) + fabsf(cj));           // rounding of the forward's coordinates and of this inverse
-        const float ei = r * (fabsf(m.ia) + fabsf(m.ib)) + slack, ej = r * (fabsf(m.ic) + fabsf(m.id)) + slack;
-        const int i_lo = static_cast<int>(fmaxf(ceilf(ci - ei), 0.f)), i_hi = static_cast<int>(fminf(floorf(ci + ei), W - 1.f));
-        const int j_lo = static_cast<int>(fmaxf(ceilf(cj - ej), 0.f)), j_hi = static_cast<int>(fminf(floorf(cj + ej), H - 1.f));
-        for (int j = j_lo; j <= j_hi; ++j) {
-            const float ys = norm_centre(j, H);
-            for (int i = i_lo; i <= i_hi; ++i) {
-                float ix, iy;
-                sample_coords_norm(th, norm_centre(i, W), ys, W, H, ix, iy);
-                float w;
-                if (nearest) {
-                    if (nearbyintf(ix) != sx || nearbyintf(iy) != sy) continue;
-                    w = 1.f;
-                } else {
-                    const float x0f = floorf(ix), y0f = floorf(iy);
-                    const float kx = sx - x0f, ky = sy - y0f;                   // which of the candidate's four neighbours this pixel is
-                    if (!((kx == 0.f || kx == 1.f) && (ky == 0.f || ky == 1.f))) continue;
-                    const float fx = ix - x0f, fy = iy - y0f;
-                    w = (kx == 0.f ? 1.f - fx : fx) * (ky == 0.f ? 1.f - fy : fy);
-                    if (w == 0.f) continue;
-                }
-                const int o = j * W + i;
-#pragma unroll
-                for (int k = 0; k < WB_M; ++k)
-                    if (k == n_match) { m_off[k] = o; m_w[k] = w; }
-                if (++n_match == WB_M) flush();
-            }
-        }
-        flush();
     }
 #pragma unroll
     for (int c = 0; c < WB_CH; ++c)
         if (c < nc) __stcs(dst + c * plane, acc[c]);
-}
-
-// scatter form of the adjoint for the maps the gather leaves out: grad_x[neighbour] += w * grad_out[pixel] (grad_x of those maps was
-// zero-filled by the gather kernel, which runs first on the same stream)
-template <int PLANE>
-__global__ void __launch_bounds__(WARP_THREADS)
-warp_backward_scatter_kernel(int C, int H, int W, const float* __restrict__ gout, long long gout_stride, const float* __restrict__ theta,
-                             const unsigned char* __restrict__ copy_mask, float* __restrict__ gx, long long gx_stride, int nearest) {
-    const int map = blockIdx.z;
-    if (copy_mask && copy_mask[map]) return;
-    if (inverse_map(theta + map * 6, W, H).gather) return;
-    const int plane = PLANE ? PLANE : H * W;
-    const int pix = blockIdx.x * WARP_THREADS + threadIdx.x;
-    if (pix >= plane) return;
-    const int c0 = blockIdx.y * WARP_CH;
-    const SamplePos s = make_sample(theta, copy_mask, map, pix, W, H, nearest);
-    const float* g = gout + map * gout_stride + static_cast<long long>(c0) * plane + pix;
-    float* dst = gx + map * gx_stride + static_cast<long long>(c0) * plane;
-    const int nc = C - c0;
-    float v[WARP_CH];
-#pragma unroll
-    for (int c = 0; c < WARP_CH; ++c) v[c] = c < nc ? __ldcs(g + c * plane) : 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (!s.ok[k] || s.w[k] == 0.f) continue;
-        float* q = dst + s.off[k];
-#pragma unroll
-        for (int c = 0; c < WARP_CH; ++c)
-            if (c < nc) atomicAdd(q + c * plane, s.w[k] * v[c]);
-    }
 }
 
 // ---- pose algebra: flow (b, T, 6) -> theta (b*T, 2, 3) -------------------------------------------------------------------
@@ -264,7 +188,6 @@ static void launch_warp_plane(int forward, dim3 grid, int C, int H, int W, const
     } else {
         const dim3 ggrid(grid.x, (C + WB_CH - 1) / WB_CH, grid.z);
         warp_backward_gather_kernel<PLANE><<<ggrid, WARP_THREADS, 0, stream>>>(C, H, W, a, a_stride, theta, copy_mask, b, b_stride, nearest);
-        warp_backward_scatter_kernel<PLANE><<<grid, WARP_THREADS, 0, stream>>>(C, H, W, a, a_stride, theta, copy_mask, b, b_stride, nearest);
     }
 }
 

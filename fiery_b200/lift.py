@@ -450,7 +450,8 @@ class LiftSplat(nn.Module):
 
 
 class _LiftWarpedFn(torch.autograd.Function):
-    """Fused forward (lift + warp epilogue); backward = adjoint of the warp (fiery_warp_features_backward), then the lift's backward."""
+    """Fused forward (lift + warp epilogue); backward = the warp's adjoint (gather kernel), then the lift's backward.  Folding the
+    adjoint into the gradient's re-layout pass was built and measured slower (profiles/r02_notes.md), so the two stay separate."""
 
     @staticmethod
     def forward(ctx, head, intrinsics, extrinsics, plan, theta, copy_mask, module):
@@ -465,7 +466,7 @@ class _LiftWarpedFn(torch.autograd.Function):
         lib = _lib.load()
         g = grad_out.float().contiguous()
         n, C, H, W = g.shape
-        g_bev = torch.empty_like(g)
+        g_bev = torch.empty_like(g)                         # overwritten by the gather adjoint
         with torch.cuda.device(g.device):
             _lib.check(lib.fiery_warp_features_backward(n, C, H, W, g.data_ptr(), C * H * W, theta.data_ptr(), copy_mask.data_ptr(),
                                                         g_bev.data_ptr(), C * H * W, 0, _stream_ptr(g.device)),

@@ -167,6 +167,7 @@ FIERY_API int fiery_lift_backward(const fiery_lift_desc_t* desc, const void* hea
                         const float* frustum_u, const float* frustum_v, const float* frustum_d,
                         const float* grad_bev, void* grad_head, float* workspace, const void* plan, void* stream);
 
+
 /*
  * Integer voxel coordinates of all N = n*D*h*w points per frame, in the reference's point order
  * (camera, depth, row, column) (fiery.py:233).  idx_out: (B',N,3) int64 = trunc((p - offset)/res) (fiery.py:236-237);
@@ -205,8 +206,8 @@ FIERY_API int fiery_voxels_summing_backward(int64_t n_rows, int32_t channels, co
  * x + m * x_map_stride (elements); channel planes are dense (H*W).  copy_mask (n_maps bytes, may be NULL): maps with a
  * non-zero byte are copied unchanged -- the present frame of a sequence (geometry.py:243).
  * backward: grad_x[m] = adjoint of the sampling applied to grad_out[m].  grad_x is OVERWRITTEN (no zero-fill needed): the adjoint
- * runs as a gather over the output pixels that sampled each source pixel (deterministic, no atomics); maps that are no near-rigid
- * transforms (|det| < 1/4, strong scaling, non-finite) fall to a scatter with atomics inside the same call.
+ * runs as a gather over the output pixels that sampled each source pixel (deterministic, no atomics); for maps that are no near-rigid
+ * transforms (|det| < 1/4, strong scaling, non-finite) the search covers the whole image: exact, but slow.
  */
 FIERY_API int fiery_warp_features_forward(int32_t n_maps, int32_t channels, int32_t height, int32_t width, const float* x,
                                           int64_t x_map_stride, const float* theta, const uint8_t* copy_mask, float* out,
