@@ -268,31 +268,6 @@ def run_train(args, cfg: LiftConfig, rank: int, local_rank: int, world: int):
         lift_only()
     ms_lift = timed(lift_only)
 
-    depth_extra = None
-    if rank == 0 and not args.no_extras:
-        from fiery_b200.depth_layer import depth_layer_forward, pack_weight as pack_depth_weight
-        n_out = cfg.head_channels
-        fh, fw = cfg.feat_hw
-        feat16 = torch.randn(frames * cfg.n_cameras, 128, fh, fw, device=dev).half()          # the backbone's output under AMP
-        wd = torch.randn(n_out, 128, 1, 1, device=dev) * 0.05
-        bd = torch.randn(n_out, device=dev)
-        wdp, wd16, bd16 = pack_depth_weight(wd, torch.float16), wd.half(), bd.half()
-        with torch.no_grad():
-            for _ in range(3):
-                depth_layer_forward(feat16, wd, bd, wdp)
-                torch.nn.functional.conv2d(feat16, wd16, bd16).float()
-            d_ms = float(np.mean(timed_steps(lambda: depth_layer_forward(feat16, wd, bd, wdp), S)))
-            dl_ms = float(np.mean(timed_steps(lambda: torch.nn.functional.conv2d(feat16, wd16, bd16), S)))
-            dlw_ms = float(np.mean(timed_steps(lambda: torch.nn.functional.conv2d(feat16, wd16, bd16).float(), S)))
-        d_bytes = feat16.numel() * 2 + feat16.shape[0] * n_out * fh * fw * 4 + 128 * 128 * 2
-        depth_extra = {"frames": frames, "ms_per_call": d_ms, "bytes": d_bytes, "achieved_gbs": d_bytes / (d_ms * 1e-3) / 1e9,
-                       "library_cudnn_fp16_ms": dl_ms, "library_cudnn_fp16_plus_widening_ms": dlw_ms,
-                       "what": "fiery_b200.depth_layer.depth_layer_forward (Encoder.depth_layer, encoder.py:36,96: persistent tcgen05 "
-                               "kind::f16 GEMM, fp16 NCHW features in, fp32 NCHW head tensor out, TMA both ways); bytes = features "
-                               "read once + head written once + weights; library lines: torch conv2d (cuDNN, fp16 out) alone and "
-                               "followed by the .float() an AMP step needs before the fp32 lift; L2 flushed before every call"}
-        del feat16
-
     def reduce_max(x):
         if not distributed:
             return x
@@ -311,7 +286,7 @@ def run_train(args, cfg: LiftConfig, rank: int, local_rank: int, world: int):
             "dtype": "f32", "data": "synthetic",
             "config": config_dict(cfg, args, world),          # identical in both arms
             "details": {"batch_per_gpu": b, "time_receptive_field": s,
-                       "precision": precision, "step": "depth_layer (cuDNN, autocast) -> fused lift forward (channels-last BEV) -> BEV head "
+                       "precision": precision, "step": "depth_layer (tcgen05 GEMM: half features -> fp32 head; backward: cuDNN) -> fused lift forward (channels-last BEV) -> BEV head "
                        "+ uncertainty-weighted losses -> fused lift backward (shared geometry plan) -> ONE all-reduce of the flat fp32 "
                        "gradient -> clip 5 -> Adam(3e-4, wd 1e-7); image backbone excluded (feature maps are the input)",
                        "parallelism": f"dp{world}: batch sharded over {world} GPU(s), single NCCL all-reduce of {trainer.bucket.nbytes} gradient bytes per step",

@@ -6,7 +6,7 @@ consumes.  ``DepthLayer`` carries the same parameters (``weight`` (C + D, 128, 1
 loads unchanged) and runs the layer as a tcgen05 GEMM (fiery_b200/csrc/depth_layer.cu) that reads the features in the dtype the
 backbone emits (fp16 / bf16 under AMP, fp32 otherwise) and writes the **fp32** head tensor directly -- the dtype the lift computes in
 (the reference's softmax and outer product run in fp32 under autocast, encoder.py:99-100), so an AMP step needs no widening pass
-between the two.  The backward (gradients of features, weight and bias) are three library GEMMs / reductions in torch.
+between the two.  The backward (gradients of features, weight and bias) is one library call, ``aten::convolution_backward``.
 No CPU path.
 """
 from __future__ import annotations
@@ -43,7 +43,9 @@ def depth_layer_forward(feat: torch.Tensor, weight: torch.Tensor, bias, packed: 
     wp = packed if packed is not None else pack_weight(weight, x.dtype)
     if wp.dtype != x.dtype or tuple(wp.shape) != (128, 128) or wp.device != x.device:
         raise ValueError("packed weights must be pack_weight(weight, feat.dtype) on the features' device")
-    b = bias.detach().float().contiguous() if bias is not None else None
+    b = None
+    if bias is not None:
+        b = bias if (bias.dtype == torch.float32 and bias.is_contiguous()) else bias.detach().float().contiguous()
     out = torch.empty((N, n_out, h, w), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         _lib.check(lib.fiery_depth_layer_forward(N, h * w, n_out, x.data_ptr(), _DTYPE_CODE[x.dtype], wp.data_ptr(),
@@ -55,26 +57,29 @@ def depth_layer_forward(feat: torch.Tensor, weight: torch.Tensor, bias, packed: 
 class _DepthLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feat, weight, bias, packed):
-        ctx.save_for_backward(feat, weight)
+        if packed is None:
+            packed = pack_weight(weight, feat.dtype)
+        ctx.save_for_backward(feat, weight, packed)
         ctx.has_bias = bias is not None
         return depth_layer_forward(feat, weight, bias, packed)
 
     @staticmethod
     def backward(ctx, g):                                  # g (N, n_out, h, w) fp32: the lift's grad_head
-        """Library GEMMs in the features' dtype -- what the reference's convolution backward runs in under autocast (half operands,
-        fp32 accumulation, loss-scaled gradients); fp32 features keep fp32 GEMMs."""
-        feat, weight = ctx.saved_tensors
+        """One library call (``aten::convolution_backward``: cuDNN data- and weight-gradient kernels) in the features' dtype -- what
+        the reference's convolution backward runs in under autocast (half operands, fp32 accumulation, loss-scaled gradients).  The
+        training step is launch-bound, so the backward is kept to a handful of dispatcher calls."""
+        feat, weight, packed = ctx.saved_tensors
         n_out = weight.shape[0]
         dt = feat.dtype
-        g2 = g.flatten(2)                                  # (N, n_out, P) fp32
-        gh = g2.to(dt)
-        g_feat = g_w = g_b = None
-        if ctx.needs_input_grad[0]:
-            g_feat = torch.matmul(weight.detach().reshape(n_out, 128).to(dt).t(), gh).view_as(feat)
-        if ctx.needs_input_grad[1]:
-            g_w = torch.matmul(gh, feat.flatten(2).transpose(1, 2)).float().sum(0).view_as(weight).to(weight.dtype)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            g_b = g2.sum((0, 2))
+        gh = g.contiguous() if g.dtype == dt else g.to(dt)
+        w_dt = packed[:n_out].view(n_out, 128, 1, 1)       # the weights already rounded to the operand type (a view: no kernel)
+        mask = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]]
+        g_feat, g_w, g_b = torch.ops.aten.convolution_backward(gh, feat, w_dt, [n_out] if ctx.has_bias else None, [1, 1], [0, 0], [1, 1],
+                                                               False, [0, 0], 1, mask)
+        if g_w is not None and g_w.dtype != weight.dtype:
+            g_w = g_w.to(weight.dtype)
+        if g_b is not None and g_b.dtype != torch.float32:
+            g_b = g_b.float()
         return g_feat, g_w, g_b, None
 
 

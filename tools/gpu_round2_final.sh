@@ -7,7 +7,8 @@ timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:logging --tb=sho
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${T}_smoke.log 2>&1; echo "smoke exit: $?" >> gpurun_out/${T}_smoke.log
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench exit: $?" >> gpurun_out/${T}_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2>> gpurun_out/${T}_bench.err
-for w in cfg3_baseline cfg4_pon cfg2_static_lss; do timeout 300 python bench.py --workload $w --no-cpu-baseline --no-extras > gpurun_out/${T}_bench_$w.json 2>> gpurun_out/${T}_bench.err; done
+timeout 400 python bench.py --workload cfg3_baseline --no-cpu-baseline > gpurun_out/${T}_bench_cfg3_baseline.json 2>> gpurun_out/${T}_bench.err
+for w in cfg4_pon cfg2_static_lss; do timeout 300 python bench.py --workload $w --no-cpu-baseline --no-extras > gpurun_out/${T}_bench_$w.json 2>> gpurun_out/${T}_bench.err; done
 timeout 300 python bench.py --layout channels_last --no-cpu-baseline --no-extras > gpurun_out/${T}_bench_channels_last.json 2>> gpurun_out/${T}_bench.err
 timeout 300 python bench.py --direction fwd_bwd --workload cfg3_baseline --head-dtype f16 > gpurun_out/${T}_bench_train_cfg3_f16.json 2>> gpurun_out/${T}_bench.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${T}_ncu_bench.log 2>&1
@@ -19,4 +20,8 @@ cap finalize_tma 8 finalize step
 cap lift_backward_kernel 1 bwd bwd
 cap lift_plan_kernel 1 plan bwd
 cap bev_conv7x7s2 2 conv conv
+cap depth_layer_kernel 2 depth_layer depth
+W=cfg3_baseline
+cap finalize_warp_kernel 4 finalize_warp step_warped
+cap warp_backward_gather_kernel 1 warp_backward warp_bwd
 tail -4 gpurun_out/${T}_pytest_gpu.log; tail -2 gpurun_out/${T}_smoke.log; tail -3 gpurun_out/${T}_bench.err; ls gpurun_out | grep -c ${T}
