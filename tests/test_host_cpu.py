@@ -173,3 +173,18 @@ def test_constants_follow_checkpoint_loads_and_in_place_edits():
     with torch.no_grad():
         b.bev_start_position[0] -= 2.0
     assert abs(float(shared._constants(cpu)["off"][0]) - (x0 - 2.0)) < 1e-6
+
+
+def test_fused_warp_entry_points_have_no_cpu_path():
+    """LiftSplat.forward_warped / birds_eye_view_features_warped (fiery.py:140-146 in one chain): CPU tensors raise, like every
+    other entry point; the sequence shape is checked before anything is launched."""
+    import torch
+    from fiery_b200.lift import LiftSplat, birds_eye_view_features_warped  # noqa: F401
+    from fiery_b200.synthetic import CONFIGS
+    cfg = CONFIGS["cfg1_tiny"]
+    lift = LiftSplat.from_config(cfg)
+    h, w = cfg.feat_hw
+    head = torch.zeros(2 * cfg.n_cameras, cfg.head_channels, h, w)
+    K, E = torch.eye(3).expand(2, cfg.n_cameras, 3, 3), torch.eye(4).expand(2, cfg.n_cameras, 4, 4)
+    with pytest.raises(Exception, match="CUDA|cuda"):
+        lift.forward_warped(head, K, E, torch.zeros(1, 2, 6), (50.0, 50.0))
