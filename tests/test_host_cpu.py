@@ -188,3 +188,39 @@ def test_fused_warp_entry_points_have_no_cpu_path():
     K, E = torch.eye(3).expand(2, cfg.n_cameras, 3, 3), torch.eye(4).expand(2, cfg.n_cameras, 4, 4)
     with pytest.raises(Exception, match="CUDA|cuda"):
         lift.forward_warped(head, K, E, torch.zeros(1, 2, 6), (50.0, 50.0))
+
+
+def test_python_sources_reference_only_defined_names():
+    """bench.py's code paths need a GPU, so a misplaced block shows up only on the box (it happened: a benchmark extra pasted into
+    run_train used a helper that lives in main).  A conservative static pass: every name a function loads must be bound somewhere in
+    that function, at module level, or be a builtin."""
+    import ast
+    import builtins
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + sorted(glob.glob(os.path.join(root, "fiery_b200", "*.py")))
+
+    def bound(node):
+        names = {n.id for n in ast.walk(node) if isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del))}
+        names |= {a.arg for n in ast.walk(node) if isinstance(n, ast.arguments)
+                  for a in n.args + n.kwonlyargs + n.posonlyargs + ([n.vararg] if n.vararg else []) + ([n.kwarg] if n.kwarg else [])}
+        names |= {n.name for n in ast.walk(node) if isinstance(n, (ast.FunctionDef, ast.ClassDef))}
+        names |= {(a.asname or a.name.split(".")[0]) for n in ast.walk(node) if isinstance(n, (ast.Import, ast.ImportFrom)) for a in n.names}
+        names |= {n.name for n in ast.walk(node) if isinstance(n, ast.ExceptHandler) and n.name}
+        return names
+
+    problems = []
+    for path in files:
+        tree = ast.parse(open(path).read())
+        module = set()
+        for node in tree.body:
+            module |= bound(node) if not isinstance(node, (ast.FunctionDef, ast.ClassDef)) else {node.name}
+        funcs = [n for n in tree.body if isinstance(n, ast.FunctionDef)]
+        funcs += [m for c in tree.body if isinstance(c, ast.ClassDef) for m in c.body if isinstance(m, ast.FunctionDef)]
+        for fn in funcs:
+            known = bound(fn) | module
+            loaded = {n.id for n in ast.walk(fn) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load)}
+            missing = sorted(x for x in loaded if x not in known and not hasattr(builtins, x))
+            if missing:
+                problems.append((os.path.basename(path), fn.name, missing))
+    assert not problems, problems
