@@ -129,3 +129,26 @@ def test_depth_layer_has_no_cpu_path():
         DepthLayer(112)(torch.zeros(1, 128, 4, 8))
     with pytest.raises(ValueError):
         DepthLayer(200)
+
+
+def test_depth_layer_packed_operand_follows_the_parameter():
+    """The (128, 128) operand of the kernel is cached per dtype and re-made when the weight changes in place (optimizer step) or is
+    loaded from a checkpoint -- the class of staleness ADVICE.md flagged for the lift's constants."""
+    import torch
+    from fiery_b200.depth_layer import DepthLayer, pack_weight
+    layer = DepthLayer(112)
+    a = layer._packed_weight(torch.float16)
+    assert tuple(a.shape) == (128, 128) and a.dtype == torch.float16
+    assert torch.equal(a[:112], layer.weight.detach().reshape(112, 128).half()) and float(a[112:].abs().max()) == 0.0
+    assert layer._packed_weight(torch.float16) is a                          # cached
+    assert layer._packed_weight(torch.bfloat16).dtype == torch.bfloat16     # one entry per operand type
+    with torch.no_grad():
+        layer.weight.mul_(3.0)
+    b = layer._packed_weight(torch.float16)
+    assert b is not a and torch.equal(b[:112], layer.weight.detach().reshape(112, 128).half())
+    other = DepthLayer(112)
+    layer.load_state_dict(other.state_dict())
+    c = layer._packed_weight(torch.float16)
+    assert c is not b and torch.equal(c, pack_weight(other.weight, torch.float16))
+    with pytest.raises(ValueError):
+        pack_weight(torch.zeros(112, 64, 1, 1), torch.float16)
