@@ -41,17 +41,17 @@ def test_fused_matches_oracle_chain_and_unfused_product(name, b, s):
     assert tuple(fused.shape) == (b, s, cfg.out_channels, X, Y) and fused.is_contiguous()
     unfused = cumulative_warp_features(lift(hd, Kd, Ed).unflatten(0, (b, s)), fd, mode="bilinear", spatial_extent=ext)
     scale = float(unfused.abs().max())
-    assert float((fused - unfused).abs().max()) <= 2e-6 * scale            # same samples, same blend; only the lift's atomics differ
+    assert float((fused - unfused).abs().max()) <= 5e-6 * scale            # same samples, same blend; only the lift's atomics differ
     exact = O.LiftOracle.from_config(cfg).lift_exact(head, K, E).unflatten(0, (b, s))
     want = W.cumulative_warp_features(exact.clone().float(), flow, mode="bilinear", spatial_extent=ext)
     assert float((fused.cpu() - want).abs().max()) <= TOL * float(want.abs().max())
     assert O.normwise_error(fused.cpu(), want) < TOL
     # the present frame passes through: it equals the plain lift of that frame to the lift's own run-to-run noise
     plain = lift(hd, Kd, Ed).unflatten(0, (b, s))
-    assert float((fused[:, -1] - plain[:, -1]).abs().max()) <= 2e-6 * scale
+    assert float((fused[:, -1] - plain[:, -1]).abs().max()) <= 5e-6 * scale
     # the scratch is all-zero again (the next call would otherwise double-count): run twice, same answer
     again = lift.forward_warped(hd, Kd, Ed, fd, ext)
-    assert float((again - fused).abs().max()) <= 2e-6 * scale
+    assert float((again - fused).abs().max()) <= 5e-6 * scale
 
 
 def test_fused_with_a_plan_and_in_several_passes():
@@ -64,15 +64,15 @@ def test_fused_with_a_plan_and_in_several_passes():
     plan = lift.plan(Kd, Ed)
     with_plan = lift.forward_warped(hd, Kd, Ed, fd, ext, plan=plan)
     scale = float(ref.abs().max())
-    assert float((with_plan - ref).abs().max()) <= 2e-6 * scale
-    assert float((lift.forward_warped(hd, Kd, Ed, fd, ext, plan=plan) - ref).abs().max()) <= 2e-6 * scale    # the plan's marks survive
+    assert float((with_plan - ref).abs().max()) <= 5e-6 * scale
+    assert float((lift.forward_warped(hd, Kd, Ed, fd, ext, plan=plan) - ref).abs().max()) <= 5e-6 * scale    # the plan's marks survive
     lib = _lib.load()
     try:
         lib.fiery_lift_set_max_chunk_frames(2)                            # 6 frames in 3 passes over a 2-frame scratch
         chunked = lift.forward_warped(hd, Kd, Ed, fd, ext)
     finally:
         lib.fiery_lift_set_max_chunk_frames(0)
-    assert float((chunked - ref).abs().max()) <= 2e-6 * scale
+    assert float((chunked - ref).abs().max()) <= 5e-6 * scale
 
 
 def test_single_frame_sequences_are_the_plain_lift():
@@ -83,7 +83,7 @@ def test_single_frame_sequences_are_the_plain_lift():
     out = lift.forward_warped(hd, Kd, Ed, torch.zeros(2, 1, 6, device=dev), (50.0, 50.0))
     plain = lift(hd, Kd, Ed)
     assert tuple(out.shape) == (2, 1, *plain.shape[1:])
-    assert float((out[:, 0] - plain).abs().max()) <= 2e-6 * float(plain.abs().max())
+    assert float((out[:, 0] - plain).abs().max()) <= 5e-6 * float(plain.abs().max())
 
 
 def test_fused_gradient_matches_the_unfused_chain():
