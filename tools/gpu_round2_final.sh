@@ -24,4 +24,5 @@ cap depth_layer_kernel 2 depth_layer depth
 W=cfg3_baseline
 cap finalize_warp_kernel 4 finalize_warp step_warped
 cap warp_backward_gather_kernel 1 warp_backward warp_bwd
-tail -4 gpurun_out/${T}_pytest_gpu.log; tail -2 gpurun_out/${T}_smoke.log; tail -3 gpurun_out/${T}_bench.err; ls gpurun_out | grep -c ${T}
+timeout 200 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/sanitize_target.py > gpurun_out/${T}_memcheck.log 2>&1; echo "memcheck exit: $?" >> gpurun_out/${T}_memcheck.log
+tail -4 gpurun_out/${T}_pytest_gpu.log; tail -2 gpurun_out/${T}_memcheck.log; tail -2 gpurun_out/${T}_smoke.log; tail -3 gpurun_out/${T}_bench.err; ls gpurun_out | grep -c ${T}
